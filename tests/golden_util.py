@@ -1,0 +1,60 @@
+"""Loads tests/golden/*.npz (written by oracle/make_golden.py from the unmodified
+reference) and rebuilds the inputs of a case.  Big MLPs are regenerated from the stored
+seed with pixel-nerf_b200/synth.py and verified against the stored checksum."""
+import importlib.util
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+synth = load_by_path("pnr_synth", os.path.join(ROOT, "pixel-nerf_b200", "synth.py"))
+oracle = load_by_path("pnr_oracle", os.path.join(ROOT, "oracle", "pnr_oracle.py"))
+
+CASE_NAMES = ["tiny", "tiny_sb2", "ns1_coarse_only", "c2_small", "c3_small", "c4_small"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    cfg = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg_")}
+    seed = int(z["seed"])
+    if cfg["store_weights"]:
+        wc = {k[3:]: t(k) for k in z.files if k.startswith("wc/")}
+        wf = {k[3:]: t(k) for k in z.files if k.startswith("wf/")} or None
+    else:
+        wc = synth.make_mlp_weights(seed + 2, cfg["d_hidden"])
+        wf = synth.make_mlp_weights(seed + 3, cfg["d_hidden"]) if cfg["fine_mlp"] else None
+    assert abs(synth.weights_checksum(wc) - float(z["wc_checksum"])) < 1e-6 * float(z["wc_checksum"]), \
+        "synthetic weight RNG drifted from the fixture generator"
+    if wf is not None:
+        assert abs(synth.weights_checksum(wf) - float(z["wf_checksum"])) < 1e-6 * float(z["wf_checksum"])
+    noise = {k[6:]: t(k) for k in z.files if k.startswith("noise_")}
+    c = t("c") if bool(z["has_c"]) else None
+    case = dict(name=name, cfg=cfg, seed=seed, src_poses=t("src_poses"), latent=t("latent"),
+                focal=t("focal"), c=c, rays=t("rays"), wc=wc, wf=wf, noise=noise,
+                ref={k: t(k) for k in z.files if k.startswith(("coarse_", "fine_", "z_", "field_", "ref_state_"))})
+    return case
+
+
+def oracle_state(case):
+    cfg = case["cfg"]
+    return oracle.encode_state(case["src_poses"].reshape(-1, 4, 4), case["focal"], case["c"],
+                               cfg["W"], cfg["H"])
+
+
+def oracle_render(case):
+    cfg = case["cfg"]
+    return oracle.render(case["rays"], case["noise"], oracle_state(case), case["latent"], case["wc"],
+                         case["wf"], cfg["NS"], cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"],
+                         white_bkgd=bool(cfg["white_bkgd"]), eval_batch_size=cfg["eval_batch_size"])
