@@ -1,0 +1,281 @@
+// C-ABI entry points of libpnr_sm100.so (see include/pnr.h).  Thin: argument checks, engine
+// selection, workspace carving, and the coarse -> fine orchestration of NeRFRenderer.forward
+// (src/render/nerf.py:251-303).  No CPU fallback: everything below launches CUDA kernels.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pnr_common.cuh"
+
+namespace pnr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- dominant-kernel profiling ----------------------------------------------------------
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;  // pairs (start, stop)
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_before(cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, s);
+  g_prof_ev.push_back(e);
+}
+void prof_after(cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, s);
+  g_prof_ev.push_back(e);
+}
+
+static int check_scene(const PnrScene* sc) {
+  PNR_CHECK_ARG(sc != nullptr, "scene is NULL");
+  PNR_CHECK_ARG(sc->latent_nhwc && sc->poses && sc->focal && sc->c, "scene pointers must not be NULL");
+  PNR_CHECK_ARG(sc->SB >= 1 && sc->NS >= 1, "SB and NS must be >= 1");
+  PNR_CHECK_ARG(sc->Hl >= 2 && sc->Wl >= 2, "latent must be at least 2x2");
+  PNR_CHECK_ARG(sc->C % 4 == 0, "latent channels must be a multiple of 4");
+  PNR_CHECK_ARG(sc->n_focal == 1 || sc->n_focal == sc->SB, "n_focal must be 1 or SB");
+  PNR_CHECK_ARG(sc->n_c == 1 || sc->n_c == sc->SB, "n_c must be 1 or SB");
+  return PNR_OK;
+}
+
+static int check_mlp(const PnrMlp* m) {
+  PNR_CHECK_ARG(m != nullptr, "mlp is NULL");
+  PNR_CHECK_ARG(m->n_blocks >= 1 && m->n_blocks <= PNR_MAX_BLOCKS, "n_blocks out of range");
+  PNR_CHECK_ARG(m->lin_in_w && m->lin_in_b && m->lin_out_w && m->lin_out_b, "lin_in/lin_out weights are NULL");
+  for (int i = 0; i < m->n_blocks; ++i) {
+    PNR_CHECK_ARG(m->fc0_w[i] && m->fc0_b[i] && m->fc1_w[i] && m->fc1_b[i], "block weights are NULL");
+    if (i < m->combine_layer) PNR_CHECK_ARG(m->lin_z_w[i] && m->lin_z_b[i], "lin_z weights are NULL");
+  }
+  return PNR_OK;
+}
+
+// engine actually used for (scene, mlp): AUTO prefers the tensor engine when it applies.
+static int resolve_engine(const PnrScene& sc, const PnrMlp& mlp, const float* proj, int engine) {
+  bool tc_ok = tc_supported(sc, mlp) && mlp.packed != nullptr && proj != nullptr;
+  if (engine == PNR_ENGINE_TC) {
+    if (!tc_ok) {
+      set_error("tensor engine unavailable for this call (needs d_hidden=512, d_latent=512, 5 blocks, "
+                "combine_layer=3, packed weights and projected latent)");
+      return PNR_ERR_UNSUPPORTED;
+    }
+    return PNR_ENGINE_TC;
+  }
+  if (engine == PNR_ENGINE_SIMT) return PNR_ENGINE_SIMT;
+  if (engine == PNR_ENGINE_AUTO) return tc_ok ? PNR_ENGINE_TC : PNR_ENGINE_SIMT;
+  set_error("unknown engine %d", engine);
+  return PNR_ERR_INVALID;
+}
+
+static size_t field_ws(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points, int engine) {
+  size_t a = simt_workspace_bytes(sc, mlp, total_points);
+  if (engine == PNR_ENGINE_SIMT) return a;
+  size_t b = tc_supported(sc, mlp) ? tc_workspace_bytes(sc, mlp, total_points) : 0;
+  if (engine == PNR_ENGINE_TC) return b;
+  return a > b ? a : b;
+}
+
+static int field_dispatch(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
+                          int64_t total_points, float* out, int engine, void* ws, size_t ws_bytes,
+                          cudaStream_t s) {
+  int e = resolve_engine(sc, mlp, proj, engine);
+  if (e < 0) return e;
+  if (e == PNR_ENGINE_TC) return tc_field_eval(sc, mlp, proj, src, total_points, out, ws, ws_bytes, s);
+  return simt_field_eval(sc, mlp, src, total_points, out, ws, ws_bytes, s);
+}
+
+}  // namespace pnr
+
+using namespace pnr;
+
+extern "C" {
+
+int pnr_abi_version(void) { return PNR_ABI_VERSION; }
+const char* pnr_last_error(void) { return g_err; }
+int64_t pnr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pnr_profile_begin(void) {
+  for (cudaEvent_t e : g_prof_ev) g_prof_pool.push_back(e);
+  g_prof_ev.clear();
+  g_prof_on = true;
+  return PNR_OK;
+}
+
+int pnr_profile_end(double* total_ms, int64_t* launches) {
+  g_prof_on = false;
+  double tot = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < g_prof_ev.size(); i += 2) {
+    PNR_CUDA(cudaEventSynchronize(g_prof_ev[i + 1]));
+    float ms = 0.f;
+    PNR_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[i], g_prof_ev[i + 1]));
+    tot += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : g_prof_ev) g_prof_pool.push_back(e);
+  g_prof_ev.clear();
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return PNR_OK;
+}
+
+int pnr_pack_latent(const float* latent_nchw, float* latent_nhwc, int32_t V, int32_t C, int32_t Hl, int32_t Wl,
+                    void* stream) {
+  PNR_CHECK_ARG(latent_nchw && latent_nhwc, "latent pointers are NULL");
+  PNR_CHECK_ARG(V >= 1 && C >= 1 && Hl >= 1 && Wl >= 1, "bad latent shape");
+  return launch_pack_latent(latent_nchw, latent_nhwc, V, C, Hl, Wl, (cudaStream_t)stream);
+}
+
+int pnr_sample_coarse(const float* rays, const float* lin_steps, const float* u_coarse, float* z, int64_t R,
+                      int32_t Kc, void* stream) {
+  PNR_CHECK_ARG(R >= 0 && Kc >= 1, "bad sizes");
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(rays && u_coarse && z, "NULL pointer");
+  return launch_sample_coarse(rays, lin_steps, u_coarse, z, R, Kc, (cudaStream_t)stream);
+}
+
+int pnr_composite(const float* rays, const float* z, const float* field, int32_t white_bkgd, float* weights,
+                  float* rgb, float* depth, int64_t R, int32_t K, void* stream) {
+  PNR_CHECK_ARG(R >= 0 && K >= 1, "bad sizes");
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(rays && z && field && rgb && depth, "NULL pointer");
+  return launch_composite(rays, z, field, white_bkgd, weights, rgb, depth, R, K, (cudaStream_t)stream);
+}
+
+int pnr_sample_fine(const float* rays, const float* z_coarse, const float* weights_coarse,
+                    const float* depth_coarse, const float* u_fine, const float* u_fine_jit,
+                    const float* n_depth, float depth_std, float* z_out, int64_t R, int32_t Kc, int32_t Kf,
+                    int32_t Kfd, void* stream) {
+  PNR_CHECK_ARG(R >= 0 && Kc >= 1 && Kf >= 1 && Kfd >= 0 && Kfd <= Kf, "bad sizes");
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(rays && z_coarse && z_out, "NULL pointer");
+  if (Kf - Kfd > 0) PNR_CHECK_ARG(weights_coarse && u_fine && u_fine_jit, "importance-sampling inputs are NULL");
+  if (Kfd > 0) PNR_CHECK_ARG(depth_coarse && n_depth, "depth-sampling inputs are NULL");
+  return launch_sample_fine(rays, z_coarse, weights_coarse, depth_coarse, u_fine, u_fine_jit, n_depth, depth_std,
+                            z_out, R, Kc, Kf, Kfd, (cudaStream_t)stream);
+}
+
+size_t pnr_field_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P, int32_t engine) {
+  if (!scene || !mlp || P < 0) return 0;
+  return field_ws(*scene, *mlp, P * scene->SB, engine);
+}
+
+int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, const float* viewdirs, float* out,
+                   int64_t P, int32_t engine, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_scene(scene))) return rc;
+  if ((rc = check_mlp(mlp))) return rc;
+  PNR_CHECK_ARG(P >= 0, "P must be >= 0");
+  if (P == 0) return PNR_OK;
+  PNR_CHECK_ARG(xyz && viewdirs && out && workspace, "NULL pointer");
+  PointSource src{};
+  src.mode = 0;
+  src.xyz = xyz;
+  src.dirs = viewdirs;
+  src.P = P;
+  src.K = 1;
+  return field_dispatch(*scene, *mlp, scene->proj_coarse, src, P * scene->SB, out, engine, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t pnr_render_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
+                                  const PnrRenderCfg* cfg, int64_t B) {
+  if (!scene || !mlp_coarse || !cfg || B < 0) return 0;
+  const int64_t R = B * scene->SB;
+  const int Kc = cfg->n_coarse, K = cfg->n_coarse + cfg->n_fine;
+  size_t b = 0;
+  b += align_up((size_t)R * K * 4 * 4, 256);   // field values of the larger pass
+  b += align_up((size_t)R * Kc * 4, 256) * 2;  // z_coarse, weights_coarse
+  b += align_up((size_t)R * K * 4, 256);       // z_fine
+  b += align_up((size_t)R * 4 * 4, 256) * 2;   // rgb/depth scratch when the caller passes NULL
+  size_t f = field_ws(*scene, *mlp_coarse, R * K, cfg->engine);
+  if (mlp_fine) {
+    size_t f2 = field_ws(*scene, *mlp_fine, R * K, cfg->engine);
+    if (f2 > f) f = f2;
+  }
+  return b + f + 4096;
+}
+
+int pnr_render(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine, const PnrRenderCfg* cfg,
+               const float* rays, const PnrNoise* noise, const PnrRenderOut* out, int64_t B, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_scene(scene))) return rc;
+  if ((rc = check_mlp(mlp_coarse))) return rc;
+  if (mlp_fine && (rc = check_mlp(mlp_fine))) return rc;
+  PNR_CHECK_ARG(cfg && noise && out, "cfg / noise / out is NULL");
+  PNR_CHECK_ARG(cfg->n_coarse >= 1 && cfg->n_fine >= 0 && cfg->n_fine_depth >= 0 &&
+                    cfg->n_fine_depth <= cfg->n_fine,
+                "bad sample counts");
+  PNR_CHECK_ARG(B >= 0, "B must be >= 0");
+  const int64_t R = B * scene->SB;
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(rays && workspace, "NULL pointer");
+  PNR_CHECK_ARG(noise->u_coarse, "u_coarse is NULL");
+  PNR_CHECK_ARG(out->rgb_coarse && out->depth_coarse, "coarse rgb/depth outputs are required");
+  const int Kc = cfg->n_coarse, Kf = cfg->n_fine, Kfd = cfg->n_fine_depth, K = Kc + Kf;
+  if (Kf > 0) PNR_CHECK_ARG(out->rgb_fine && out->depth_fine, "fine rgb/depth outputs are required");
+  if (workspace_bytes < pnr_render_workspace_bytes(scene, mlp_coarse, mlp_fine, cfg, B)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes,
+              pnr_render_workspace_bytes(scene, mlp_coarse, mlp_fine, cfg, B));
+    return PNR_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  float* field = ar.take<float>((size_t)R * K * 4);
+  float* zc = out->z_coarse ? out->z_coarse : ar.take<float>((size_t)R * Kc);
+  float* wc = out->weights_coarse ? out->weights_coarse : ar.take<float>((size_t)R * Kc);
+  float* zf = nullptr;
+  if (Kf > 0) zf = out->z_fine ? out->z_fine : ar.take<float>((size_t)R * K);
+  char* rest = ar.base + align_up(ar.off, 256);
+  size_t rest_bytes = workspace_bytes - align_up(ar.off, 256);
+
+  // ---- coarse pass (nerf.py:273-276) ----
+  if ((rc = launch_sample_coarse(rays, noise->lin_steps, noise->u_coarse, zc, R, Kc, s))) return rc;
+  PointSource src{};
+  src.mode = 1;
+  src.rays = rays;
+  src.z = zc;
+  src.K = Kc;
+  src.P = B * Kc;
+  if ((rc = field_dispatch(*scene, *mlp_coarse, scene->proj_coarse, src, R * Kc, field, cfg->engine, rest,
+                           rest_bytes, s)))
+    return rc;
+  if ((rc = launch_composite(rays, zc, field, cfg->white_bkgd, wc, out->rgb_coarse, out->depth_coarse, R, Kc, s)))
+    return rc;
+  if (Kf == 0) return PNR_OK;
+
+  // ---- fine pass (nerf.py:284-301) ----
+  if (Kf - Kfd > 0) PNR_CHECK_ARG(noise->u_fine && noise->u_fine_jit, "u_fine / u_fine_jit is NULL");
+  if (Kfd > 0) PNR_CHECK_ARG(noise->n_depth, "n_depth is NULL");
+  if ((rc = launch_sample_fine(rays, zc, wc, out->depth_coarse, noise->u_fine, noise->u_fine_jit, noise->n_depth,
+                               cfg->depth_std, zf, R, Kc, Kf, Kfd, s)))
+    return rc;
+  const PnrMlp* mf = mlp_fine ? mlp_fine : mlp_coarse;  // models.py:242
+  const float* pf = mlp_fine ? scene->proj_fine : scene->proj_coarse;
+  src.z = zf;
+  src.K = K;
+  src.P = B * K;
+  if ((rc = field_dispatch(*scene, *mf, pf, src, R * K, field, cfg->engine, rest, rest_bytes, s))) return rc;
+  return launch_composite(rays, zf, field, cfg->white_bkgd, out->weights_fine, out->rgb_fine, out->depth_fine, R, K,
+                          s);
+}
+
+}  // extern "C"

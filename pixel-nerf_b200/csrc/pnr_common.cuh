@@ -1,0 +1,102 @@
+// Internal helpers shared by the libpnr_sm100 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pnr.h"
+
+namespace pnr {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PNR_CHECK_ARG(cond, msg)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      pnr::set_error("invalid argument: %s", msg);    \
+      return PNR_ERR_INVALID;                         \
+    }                                                 \
+  } while (0)
+
+#define PNR_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      pnr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PNR_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define PNR_LAUNCH_CHECK()                                                             \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      pnr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PNR_ERR_CUDA;                                                             \
+    }                                                                                  \
+    pnr::count_launch();                                                               \
+  } while (0)
+
+// dominant-kernel profiling (pnr_profile_begin/end): bracket a launch with events
+void prof_before(cudaStream_t s);
+void prof_after(cudaStream_t s);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// Where the points of a field evaluation come from.
+//   mode 0: explicit xyz / viewdirs arrays [SB][P][3]            (PixelNeRFNet.forward callers)
+//   mode 1: rays [SB*B][8] and z [SB*B][K]; point (sb, p): ray = sb*B + p / K, sample = p % K
+//           (NeRFRenderer.composite, src/render/nerf.py:185-211)
+struct PointSource {
+  int mode;
+  const float* xyz;
+  const float* dirs;
+  const float* rays;
+  const float* z;
+  int K;          // samples per ray (mode 1)
+  int64_t P;      // points per object
+};
+
+// ---- stage launchers (pnr_stages.cu, compiled with -fmad=false) -------------------------
+int launch_pack_latent(const float* nchw, float* nhwc, int V, int C, int Hl, int Wl, cudaStream_t s);
+int launch_sample_coarse(const float* rays, const float* lin, const float* u, float* z, int64_t R, int Kc,
+                         cudaStream_t s);
+int launch_composite(const float* rays, const float* z, const float* field, int white, float* w,
+                     float* rgb, float* depth, int64_t R, int K, cudaStream_t s);
+int launch_sample_fine(const float* rays, const float* zc, const float* wc, const float* dc,
+                       const float* u, const float* uj, const float* nd, float depth_std, float* zout,
+                       int64_t R, int Kc, int Kf, int Kfd, cudaStream_t s);
+// rows of a point chunk: feat [rows][48] (42 used) and gathered latent lat [rows][C];
+// row = local_point * NS + view.  g0 = first global point (sb*P + p), n_pts points.
+int launch_build_rows(const PnrScene& sc, const PointSource& src, int64_t g0, int64_t n_pts, float* feat,
+                      float* lat, cudaStream_t s);
+
+// ---- SIMT engine (pnr_field_simt.cu) ---------------------------------------------------
+size_t simt_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);
+int simt_field_eval(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src, int64_t total_points,
+                    float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// ---- tensor engine (pnr_field_tc.cu) ---------------------------------------------------
+bool tc_supported(const PnrScene& sc, const PnrMlp& mlp);
+size_t tc_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);
+int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
+                  int64_t total_points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+
+}  // namespace pnr

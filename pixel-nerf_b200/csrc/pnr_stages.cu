@@ -1,0 +1,333 @@
+// Per-ray / per-point stage kernels of the render path: latent re-layout, stratified and
+// importance sampling, point feature construction (camera transform, positional code,
+// projection, bilinear border gather) and alpha compositing.
+//
+// This file is compiled with -fmad=false: the reference evaluates these stages as separate
+// elementwise torch ops (one rounding per op), and reproducing that rounding keeps the
+// stochastic fine sampler (searchsorted bin edges) aligned with it.
+#include <math.h>
+
+#include "pnr_common.cuh"
+
+namespace pnr {
+
+// ----------------------------------------------------------------------------------------
+// NCHW -> NHWC (reference keeps NCHW and pays a strided gather: encoder.py:102, models.py:219)
+// ----------------------------------------------------------------------------------------
+__global__ void k_pack_latent(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int v = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* s = src + (size_t)v * C * HW;
+  float* d = dst + (size_t)v * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) d[(size_t)p * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+int launch_pack_latent(const float* nchw, float* nhwc, int V, int C, int Hl, int Wl, cudaStream_t s) {
+  int HW = Hl * Wl;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, V), block(32, 8);
+  k_pack_latent<<<grid, block, 0, s>>>(nchw, nhwc, C, HW);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// sample_coarse (src/render/nerf.py:98-113)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float lin_step_value(int k, int Kc) {
+  // torch.linspace(0, 1 - 1/Kc, Kc) in fp32 (symmetric two-sided formula of ATen)
+  float step_sz = 1.0f / (float)Kc;
+  float end = 1.0f - step_sz;
+  float inc = (Kc > 1) ? end / (float)(Kc - 1) : 0.f;
+  return (k < Kc / 2) ? inc * (float)k : end - inc * (float)(Kc - 1 - k);
+}
+
+__global__ void k_sample_coarse(const float* __restrict__ rays, const float* __restrict__ lin,
+                                const float* __restrict__ u, float* __restrict__ z, int64_t R, int Kc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Kc) return;
+  int64_t r = i / Kc;
+  int k = (int)(i - r * Kc);
+  float near = rays[r * 8 + 6], far = rays[r * 8 + 7];
+  float step = 1.0f / (float)Kc;  // python float 1.0/Kc rounded to fp32 on use
+  float s = lin ? lin[k] : lin_step_value(k, Kc);
+  s = s + u[i] * step;            // z_steps += rand_like * step
+  z[i] = near * (1.0f - s) + far * s;
+}
+
+int launch_sample_coarse(const float* rays, const float* lin, const float* u, float* z, int64_t R, int Kc,
+                         cudaStream_t s) {
+  int64_t n = R * Kc;
+  if (n == 0) return PNR_OK;
+  k_sample_coarse<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rays, lin, u, z, R, Kc);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// compositing (src/render/nerf.py:178-182, 222-249).  One thread per ray; K is small.
+// ----------------------------------------------------------------------------------------
+__global__ void k_composite(const float* __restrict__ rays, const float* __restrict__ z,
+                            const float* __restrict__ field, int white, float* __restrict__ w_out,
+                            float* __restrict__ rgb_out, float* __restrict__ depth_out, int64_t R, int K) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float far = rays[r * 8 + 7];
+  const float* zr = z + r * K;
+  const float4* fr = reinterpret_cast<const float4*>(field) + r * K;
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, wsum = 0.f;
+  float zk = zr[0];
+  for (int k = 0; k < K; ++k) {
+    float znext = (k + 1 < K) ? zr[k + 1] : far;
+    float delta = znext - zk;
+    float4 f = fr[k];
+    float sigma = fmaxf(f.w, 0.f);
+    float alpha = 1.0f - expf(-delta * sigma);
+    float w = alpha * T;
+    T = T * ((1.0f - alpha) + 1e-10f);
+    cr += w * f.x;
+    cg += w * f.y;
+    cb += w * f.z;
+    cd += w * zk;
+    wsum += w;
+    if (w_out) w_out[r * K + k] = w;
+    zk = znext;
+  }
+  if (white) {
+    cr = (cr + 1.0f) - wsum;
+    cg = (cg + 1.0f) - wsum;
+    cb = (cb + 1.0f) - wsum;
+  }
+  rgb_out[r * 3 + 0] = cr;
+  rgb_out[r * 3 + 1] = cg;
+  rgb_out[r * 3 + 2] = cb;
+  depth_out[r] = cd;
+}
+
+int launch_composite(const float* rays, const float* z, const float* field, int white, float* w,
+                     float* rgb, float* depth, int64_t R, int K, cudaStream_t s) {
+  if (R == 0) return PNR_OK;
+  k_composite<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(rays, z, field, white, w, rgb, depth, R, K);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// sample_fine + sample_fine_depth + cat + sort (src/render/nerf.py:120-161, 285-295)
+// One warp per ray.  cdf is accumulated sequentially (torch.cumsum order on CPU).
+// ----------------------------------------------------------------------------------------
+constexpr int kMaxK = 512;  // Kc + Kf upper bound for the shared-memory sorter
+
+__global__ void k_sample_fine(const float* __restrict__ rays, const float* __restrict__ zc,
+                              const float* __restrict__ wc, const float* __restrict__ dc,
+                              const float* __restrict__ u, const float* __restrict__ uj,
+                              const float* __restrict__ nd, float depth_std, float* __restrict__ zout,
+                              int64_t R, int Kc, int Kf, int Kfd) {
+  extern __shared__ float sm[];
+  const int warps = blockDim.x / 32;
+  const int wid = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int K = Kc + Kf;
+  float* cdf = sm + (size_t)wid * (Kc + 1 + K);  // [Kc+1]
+  float* zs = cdf + (Kc + 1);                     // [K]
+  int64_t r = (int64_t)blockIdx.x * warps + wid;
+  if (r >= R) return;
+  const float near = rays[r * 8 + 6], far = rays[r * 8 + 7];
+  const int Ku = Kf - Kfd;
+
+  for (int k = lane; k < Kc; k += 32) zs[k] = zc[r * Kc + k];
+  if (Ku > 0) {
+    // pdf = (w + 1e-5) / sum ; cdf = [0, cumsum(pdf)]
+    float part = 0.f;
+    for (int k = lane; k < Kc; k += 32) part += wc[r * Kc + k] + 1e-5f;
+    // torch.sum order is not sequential either; use a fixed tree so results are deterministic
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float total = part;
+    if (lane == 0) {
+      float acc = 0.f;
+      cdf[0] = 0.f;
+      for (int k = 0; k < Kc; ++k) {
+        acc += (wc[r * Kc + k] + 1e-5f) / total;
+        cdf[k + 1] = acc;
+      }
+    }
+    __syncwarp();
+    for (int j = lane; j < Ku; j += 32) {
+      float uu = u[r * Ku + j];
+      // searchsorted(cdf, u, right=True): number of entries <= u  (cdf is non-decreasing)
+      int lo = 0, hi = Kc + 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      float ind = fmaxf((float)lo - 1.0f, 0.f);
+      float s = (ind + uj[r * Ku + j]) / (float)Kc;
+      zs[Kc + j] = near * (1.0f - s) + far * s;
+    }
+  }
+  if (Kfd > 0) {
+    float d = dc[r];
+    for (int j = lane; j < Kfd; j += 32) {
+      float zz = d + nd[r * Kfd + j] * depth_std;
+      zs[Kc + Ku + j] = fmaxf(fminf(zz, far), near);
+    }
+  }
+  __syncwarp();
+  // rank sort (values only matter; ties broken by index)
+  for (int i = lane; i < K; i += 32) {
+    float v = zs[i];
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+      float o = zs[j];
+      rank += (o < v) || (o == v && j < i);
+    }
+    zout[r * K + rank] = v;
+  }
+}
+
+int launch_sample_fine(const float* rays, const float* zc, const float* wc, const float* dc,
+                       const float* u, const float* uj, const float* nd, float depth_std, float* zout,
+                       int64_t R, int Kc, int Kf, int Kfd, cudaStream_t s) {
+  if (R == 0) return PNR_OK;
+  const int warps = 4;
+  size_t smem = (size_t)warps * (Kc + 1 + Kc + Kf) * sizeof(float);
+  if (Kc + Kf > kMaxK) {
+    set_error("n_coarse + n_fine = %d exceeds %d", Kc + Kf, kMaxK);
+    return PNR_ERR_INVALID;
+  }
+  k_sample_fine<<<(unsigned)((R + warps - 1) / warps), warps * 32, smem, s>>>(
+      rays, zc, wc, dc, u, uj, nd, depth_std, zout, R, Kc, Kf, Kfd);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// Point rows: camera transform, positional code, projection, bilinear border gather
+// (src/model/models.py:158-227, src/model/code.py:30-42, src/model/encoder.py:80-109)
+// ----------------------------------------------------------------------------------------
+struct PointGeom {
+  float q[3];    // R x            (z_feature input, normalize_z: models.py:171)
+  float dcam[3]; // R dir          (models.py:188-193)
+  float w_nw, w_ne, w_sw, w_se;
+  int x0, y0, x1, y1;
+};
+
+__device__ __forceinline__ void load_point(const PointSource& src, int64_t g, float x[3], float d[3]) {
+  if (src.mode == 0) {
+    for (int i = 0; i < 3; ++i) {
+      x[i] = src.xyz[g * 3 + i];
+      d[i] = src.dirs ? src.dirs[g * 3 + i] : 0.f;
+    }
+  } else {
+    int64_t ray = g / src.K;
+    int k = (int)(g - ray * src.K);
+    const float* rr = src.rays + ray * 8;
+    float zz = src.z[ray * src.K + k];
+    for (int i = 0; i < 3; ++i) {
+      d[i] = rr[3 + i];
+      x[i] = rr[i] + zz * d[i];  // nerf.py:185
+    }
+  }
+}
+
+__device__ __forceinline__ PointGeom point_geometry(const PnrScene& sc, int sb, int v, const float x[3],
+                                                    const float d[3]) {
+  PointGeom g;
+  const float* M = sc.poses + (size_t)(sb * sc.NS + v) * 12;
+  float p[3];
+  for (int i = 0; i < 3; ++i) {
+    g.q[i] = (M[i * 4 + 0] * x[0] + M[i * 4 + 1] * x[1]) + M[i * 4 + 2] * x[2];
+    p[i] = g.q[i] + M[i * 4 + 3];
+    g.dcam[i] = (M[i * 4 + 0] * d[0] + M[i * 4 + 1] * d[1]) + M[i * 4 + 2] * d[2];
+  }
+  const float* fo = sc.focal + (sc.n_focal > 1 ? sb * 2 : 0);
+  const float* cc = sc.c + (sc.n_c > 1 ? sb * 2 : 0);
+  float u = (-p[0] / p[2]) * fo[0] + cc[0];   // models.py:206-212
+  float w = (-p[1] / p[2]) * fo[1] + cc[1];
+  // encoder.py:96-99: uv * (latent_scaling / image_size) - 1
+  float gx = u * (sc.scale_x / sc.image_w) - 1.0f;
+  float gy = w * (sc.scale_y / sc.image_h) - 1.0f;
+  // grid_sample(align_corners=True): ((g + 1) / 2) * (size - 1), then border clip
+  float ix = ((gx + 1.0f) / 2.0f) * (float)(sc.Wl - 1);
+  float iy = ((gy + 1.0f) / 2.0f) * (float)(sc.Hl - 1);
+  ix = fminf((float)(sc.Wl - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(sc.Hl - 1), fmaxf(iy, 0.f));
+  // NaN coordinates (point exactly on a camera plane) clip to 0 like ATen's clip_coordinates
+  if (!(ix == ix)) ix = 0.f;
+  if (!(iy == iy)) iy = 0.f;
+  float x0 = floorf(ix), y0 = floorf(iy);
+  float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  g.w_nw = (x1 - ix) * (y1 - iy);
+  g.w_ne = (ix - x0) * (y1 - iy);
+  g.w_sw = (x1 - ix) * (iy - y0);
+  g.w_se = (ix - x0) * (iy - y0);
+  g.x0 = (int)x0;
+  g.y0 = (int)y0;
+  g.x1 = min((int)x1, sc.Wl - 1);  // out-of-range taps carry weight 0
+  g.y1 = min((int)y1, sc.Hl - 1);
+  if ((int)x1 > sc.Wl - 1) { g.w_ne = 0.f; g.w_se = 0.f; }
+  if ((int)y1 > sc.Hl - 1) { g.w_sw = 0.f; g.w_se = 0.f; }
+  return g;
+}
+
+__device__ __forceinline__ float feat_channel(const PointGeom& g, int ch) {
+  // [q(3) | for k<6: sin(q f_k)(3), sin(q f_k + pi/2)(3) | R dir (3)], f_k = 1.5 * 2^k
+  if (ch < 3) return g.q[ch];
+  if (ch < 39) {
+    int j = (ch - 3) / 3, c = (ch - 3) % 3;
+    float f = 1.5f * (float)(1 << (j >> 1));
+    float ph = (j & 1) ? 1.57079637050628662109375f : 0.f;  // fp32(pi/2), code.py:27
+    return sinf(ph + g.q[c] * f);                           // addcmul(phases, x, freqs)
+  }
+  if (ch < 42) return g.dcam[ch - 39];
+  return 0.f;
+}
+
+__global__ void k_build_rows(PnrScene sc, PointSource src, int64_t g0, int64_t n_pts,
+                             float* __restrict__ feat, float* __restrict__ lat) {
+  const int lane = threadIdx.x % 32;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (row >= n_pts * sc.NS) return;
+  int64_t lp = row / sc.NS;
+  int v = (int)(row - lp * sc.NS);
+  int64_t g = g0 + lp;
+  int sb = (int)(g / src.P);
+  float x[3], d[3];
+  load_point(src, g, x, d);
+  PointGeom pg = point_geometry(sc, sb, v, x, d);
+  for (int ch = lane; ch < 48; ch += 32) feat[row * 48 + ch] = feat_channel(pg, ch);
+  const float* L = sc.latent_nhwc + (size_t)(sb * sc.NS + v) * sc.Hl * sc.Wl * sc.C;
+  const float4* t00 = reinterpret_cast<const float4*>(L + ((size_t)pg.y0 * sc.Wl + pg.x0) * sc.C);
+  const float4* t01 = reinterpret_cast<const float4*>(L + ((size_t)pg.y0 * sc.Wl + pg.x1) * sc.C);
+  const float4* t10 = reinterpret_cast<const float4*>(L + ((size_t)pg.y1 * sc.Wl + pg.x0) * sc.C);
+  const float4* t11 = reinterpret_cast<const float4*>(L + ((size_t)pg.y1 * sc.Wl + pg.x1) * sc.C);
+  float4* o = reinterpret_cast<float4*>(lat + row * sc.C);
+  for (int c4 = lane; c4 < sc.C / 4; c4 += 32) {
+    float4 a = __ldg(t00 + c4), b = __ldg(t01 + c4), c = __ldg(t10 + c4), e = __ldg(t11 + c4);
+    float4 r;
+    r.x = ((a.x * pg.w_nw + b.x * pg.w_ne) + c.x * pg.w_sw) + e.x * pg.w_se;
+    r.y = ((a.y * pg.w_nw + b.y * pg.w_ne) + c.y * pg.w_sw) + e.y * pg.w_se;
+    r.z = ((a.z * pg.w_nw + b.z * pg.w_ne) + c.z * pg.w_sw) + e.z * pg.w_se;
+    r.w = ((a.w * pg.w_nw + b.w * pg.w_ne) + c.w * pg.w_sw) + e.w * pg.w_se;
+    o[c4] = r;
+  }
+}
+
+int launch_build_rows(const PnrScene& sc, const PointSource& src, int64_t g0, int64_t n_pts, float* feat,
+                      float* lat, cudaStream_t s) {
+  int64_t rows = n_pts * sc.NS;
+  if (rows == 0) return PNR_OK;
+  const int warps = 8;
+  k_build_rows<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, s>>>(sc, src, g0, n_pts, feat, lat);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+}  // namespace pnr

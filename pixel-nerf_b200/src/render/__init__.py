@@ -1,0 +1,2 @@
+"""Drop-in for the reference's `render` package (src/render/__init__.py)."""
+from .nerf import NeRFRenderer  # noqa: F401

@@ -1,0 +1,337 @@
+"""
+NeRFRenderer with the reference's surface (src/render/nerf.py): `from_conf`, `forward(model,
+rays, want_weights)`, `bind_parallel(net, gpus, simple_output)`, `sched_step`, mutable
+`n_coarse / n_fine / using_fine / eval_batch_size`, persistent `iter_idx / last_sched`.
+
+Inference with a PixelNeRFNet on CUDA runs the whole sample -> field -> composite ->
+resample -> field -> composite chain in one C-ABI call (`pnr_render`, include/pnr.h); the
+random draws are made here with torch, in the reference's order, and handed to the kernels,
+so a seeded run replays the reference's samples.  With autograd enabled (training) or a
+foreign `model` callable the renderer uses the composed torch path below.
+
+Multi-GPU (`bind_parallel(net, gpus)`): the reference wraps a `DataParallel(dim=1)`, which
+re-broadcasts the whole module on every call; `_ShardedRender` instead keeps one replica of
+the derived device state per GPU (refreshed only when encode()/weights change) and slices
+rays with torch.chunk semantics, so ray order in the gathered output is identical.
+"""
+import copy
+
+import torch
+
+import pnr_native as pn
+
+from .dotmap_compat import DotMap
+
+
+# ------------------------------------------------------------------------------------------
+# composed torch path (autograd / generic model callables)
+# ------------------------------------------------------------------------------------------
+def _stratified(rays, n, u):
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    s = torch.linspace(0, 1 - 1.0 / n, n, device=rays.device).unsqueeze(0).repeat(rays.shape[0], 1)
+    s = s + u * (1.0 / n)
+    return near * (1 - s) + far * s
+
+
+def _importance(rays, weights, u, jitter, n_coarse):
+    w = weights.detach() + 1e-5
+    cdf = torch.cumsum(w / torch.sum(w, -1, keepdim=True), -1)
+    cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
+    bins = torch.clamp_min(torch.searchsorted(cdf, u, right=True).float() - 1.0, 0.0)
+    s = (bins + jitter) / n_coarse
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    return near * (1 - s) + far * s
+
+
+def _around_depth(rays, depth, noise, std):
+    z = depth.unsqueeze(1).repeat((1, noise.shape[1])) + noise * std
+    return torch.max(torch.min(z, rays[:, 7:8]), rays[:, 6:7])
+
+
+def _integrate(rays, z, field, white_bkgd):
+    delta = torch.cat([z[:, 1:] - z[:, :-1], rays[:, 7:8] - z[:, -1:]], -1)
+    alpha = 1 - torch.exp(-delta * torch.relu(field[..., 3]))
+    trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1 - alpha + 1e-10], -1), -1)
+    w = alpha * trans[:, :-1]
+    rgb = torch.sum(w.unsqueeze(-1) * field[..., :3], -2)
+    depth = torch.sum(w * z, -1)
+    if white_bkgd:
+        rgb = rgb + 1 - w.sum(dim=1).unsqueeze(-1)
+    return w, rgb, depth
+
+
+class _RenderWrapper(torch.nn.Module):
+    """Callable returned by bind_parallel (nerf.py:15-42)."""
+
+    def __init__(self, net, renderer, simple_output):
+        super().__init__()
+        self.net = net
+        self.renderer = renderer
+        self.simple_output = simple_output
+
+    def forward(self, rays, want_weights=False):
+        if rays.shape[0] == 0:
+            return torch.zeros(0, 3, device=rays.device), torch.zeros(0, device=rays.device)
+        outputs = self.renderer(self.net, rays, want_weights=want_weights and not self.simple_output)
+        if self.simple_output:
+            best = outputs.fine if self.renderer.using_fine else outputs.coarse
+            return best.rgb, best.depth
+        return outputs.toDict()
+
+
+class _ShardedRender(torch.nn.Module):
+    """Single-process ray sharding over several GPUs (replaces nn.DataParallel(dim=1),
+    nerf.py:368-370).  Shard i gets torch.chunk piece i of the rays along dim 1; kernels on all
+    devices are enqueued from this thread (launches are asynchronous) and results are copied
+    to gpus[0] in shard order."""
+
+    def __init__(self, wrapped, gpus):
+        super().__init__()
+        self.module = wrapped
+        self.gpus = [int(g) for g in gpus]
+        self._replicas = {}
+        self._key = None
+
+    def _refresh(self):
+        net = self.module.net
+        key = (tuple((p.data_ptr(), p._version) for p in net.parameters()),
+               net.encoder.latent.data_ptr(), net.encoder.latent._version, net.poses.data_ptr(),
+               net.num_views_per_obj)
+        if key == self._key:
+            return
+        self._replicas = {}
+        for g in self.gpus[1:]:
+            dev = torch.device("cuda", g)
+            fused, net._fused = net._fused, None   # derived device state is rebuilt per replica
+            try:
+                rep = copy.deepcopy(net).to(dev)   # encode() buffers are registered, so they follow
+            finally:
+                net._fused = fused
+            rep._fused = type(fused)()
+            rep.num_objs, rep.num_views_per_obj = net.num_objs, net.num_views_per_obj
+            rep._image_wh = net._image_wh
+            rep.eval()
+            self._replicas[g] = _RenderWrapper(rep, self.module.renderer, self.module.simple_output)
+        self._key = key
+
+    def forward(self, rays, want_weights=False):
+        self._refresh()
+        dev0 = torch.device("cuda", self.gpus[0])
+        pieces = torch.chunk(rays, len(self.gpus), dim=1)
+        results = []
+        for g, piece in zip(self.gpus, pieces):
+            dev = torch.device("cuda", g)
+            mod = self.module if g == self.gpus[0] else self._replicas[g]
+            with torch.cuda.device(dev):
+                results.append(mod(piece.to(dev, non_blocking=True), want_weights=want_weights))
+        return _gather(results, dev0)
+
+
+def _gather(results, dev):
+    first = results[0]
+    if isinstance(first, dict):
+        return {k: _gather([r[k] for r in results], dev) for k in first}
+    if isinstance(first, (tuple, list)):
+        return type(first)(_gather([r[i] for r in results], dev) for i in range(len(first)))
+    return torch.cat([r.to(dev, non_blocking=True) for r in results], dim=1)
+
+
+class NeRFRenderer(torch.nn.Module):
+    def __init__(self, n_coarse=128, n_fine=0, n_fine_depth=0, noise_std=0.0, depth_std=0.01,
+                 eval_batch_size=100000, white_bkgd=False, lindisp=False, sched=None):
+        super().__init__()
+        if lindisp:
+            raise NotImplementedError("lindisp = True is not supported (no shipped dataset uses it)")
+        self.n_coarse, self.n_fine, self.n_fine_depth = n_coarse, n_fine, n_fine_depth
+        self.noise_std, self.depth_std = noise_std, depth_std
+        self.eval_batch_size = eval_batch_size
+        self.white_bkgd = white_bkgd
+        self.lindisp = lindisp
+        self.using_fine = n_fine > 0
+        self.sched = sched if (sched is not None and len(sched) > 0) else None
+        self.register_buffer("iter_idx", torch.tensor(0, dtype=torch.long), persistent=True)
+        self.register_buffer("last_sched", torch.tensor(0, dtype=torch.long), persistent=True)
+        self._lin_cache = {}
+
+    # -- sampling helpers with the reference's names (used by the torch path and by callers) --
+    def sample_coarse(self, rays):
+        return _stratified(rays, self.n_coarse, torch.rand(rays.shape[0], self.n_coarse, device=rays.device))
+
+    def sample_fine(self, rays, weights):
+        B, n = rays.shape[0], self.n_fine - self.n_fine_depth
+        u = torch.rand(B, n, dtype=torch.float32, device=rays.device)
+        return _importance(rays, weights, u, torch.rand_like(u), self.n_coarse)
+
+    def sample_fine_depth(self, rays, depth):
+        noise = torch.randn(rays.shape[0], self.n_fine_depth, device=rays.device)
+        return _around_depth(rays, depth, noise, self.depth_std)
+
+    def composite(self, model, rays, z_samp, coarse=True, sb=0):
+        """Query `model` at the samples in point chunks and integrate (nerf.py:163-249)."""
+        B, K = z_samp.shape
+        pts = rays[:, None, :3] + z_samp.unsqueeze(2) * rays[:, None, 3:6]
+        dirs = rays[:, None, 3:6].expand(-1, K, -1)
+        if sb > 0:
+            pts, dirs, dim, chunk = pts.reshape(sb, -1, 3), dirs.reshape(sb, -1, 3), 1, (self.eval_batch_size - 1) // sb + 1
+        else:
+            pts, dirs, dim, chunk = pts.reshape(-1, 3), dirs.reshape(-1, 3), 0, self.eval_batch_size
+        use_dirs = getattr(model, "use_viewdirs", False)
+        vals = []
+        for p, d in zip(torch.split(pts, chunk, dim=dim), torch.split(dirs, chunk, dim=dim)):
+            vals.append(model(p, coarse=coarse, viewdirs=d) if use_dirs else model(p, coarse=coarse))
+        field = torch.cat(vals, dim=dim).reshape(B, K, -1)
+        if self.training and self.noise_std > 0.0:
+            field = torch.cat((field[..., :3], field[..., 3:4] + torch.randn_like(field[..., 3:4]) * self.noise_std), -1)
+        return _integrate(rays, z_samp, field, self.white_bkgd)
+
+    # ------------------------------------------------------------------------------------
+    def forward(self, model, rays, want_weights=False):
+        """rays (SB,B,8) -> DotMap(coarse=DotMap(rgb,depth[,weights]), fine=...) (nerf.py:251-303)."""
+        if self.sched is not None and self.last_sched.item() > 0:
+            self.n_coarse = self.sched[1][self.last_sched.item() - 1]
+            self.n_fine = self.sched[2][self.last_sched.item() - 1]
+        assert rays.dim() == 3
+        if self._can_fuse(model, rays):
+            return self._forward_fused(model, rays, want_weights)
+        return self._forward_torch(model, rays, want_weights)
+
+    def _can_fuse(self, model, rays):
+        from model.models import PixelNeRFNet
+        if not isinstance(model, PixelNeRFNet):
+            return False
+        if model._needs_autograd(rays):
+            return False
+        if self.training and self.noise_std > 0.0:
+            raise NotImplementedError("noise_std > 0 in training mode is not supported by the fused path")
+        return True
+
+    def _forward_torch(self, model, rays, want_weights):
+        sb = rays.shape[0]
+        flat = rays.reshape(-1, 8)
+        z_c = self.sample_coarse(flat)
+        comp_c = self.composite(model, flat, z_c, coarse=True, sb=sb)
+        out = DotMap(coarse=self._format_outputs(comp_c, sb, want_weights))
+        if self.using_fine:
+            zs = [z_c]
+            if self.n_fine - self.n_fine_depth > 0:
+                zs.append(self.sample_fine(flat, comp_c[0].detach()))
+            if self.n_fine_depth > 0:
+                zs.append(self.sample_fine_depth(flat, comp_c[2]))
+            z_all, _ = torch.sort(torch.cat(zs, dim=-1), dim=-1)
+            comp_f = self.composite(model, flat, z_all, coarse=False, sb=sb)
+            out.fine = self._format_outputs(comp_f, sb, want_weights)
+        return out
+
+    def _lin_steps(self, n, device):
+        key = (n, str(device))
+        t = self._lin_cache.get(key)
+        if t is None:
+            t = torch.linspace(0, 1 - 1.0 / n, n, device=device)
+            self._lin_cache[key] = t
+        return t
+
+    def _forward_fused(self, model, rays, want_weights, noise_in=None, want_z=False):
+        """noise_in: optional dict(u_coarse, u_fine, u_fine_jit, n_depth) replacing the torch draws
+        (parity tests replay a fixture's noise); want_z also returns the sample depths."""
+        dev = rays.device
+        if not rays.is_cuda:
+            raise RuntimeError("the fused render path needs CUDA rays (no CPU fallback); got %s" % dev)
+        SB, B, _ = rays.shape
+        R = SB * B
+        Kc, Kf, Kfd = int(self.n_coarse), int(self.n_fine), int(self.n_fine_depth)
+        fine = bool(self.using_fine) and Kf > 0
+        if not fine:
+            Kf = Kfd = 0
+        rays_c = rays.detach().contiguous().float()
+        f32 = dict(dtype=torch.float32, device=dev)
+        # random draws in the reference's order (nerf.py:111,135,141,158)
+        noise = pn.PnrNoise()
+        lin = self._lin_steps(Kc, dev)
+        draw = noise_in is None
+        u_c = torch.rand(R, Kc, **f32) if draw else noise_in["u_coarse"].to(**f32).contiguous()
+        noise.lin_steps, noise.u_coarse = pn.dptr(lin), pn.dptr(u_c)
+        keep = [lin, u_c]
+        if fine and Kf - Kfd > 0:
+            u_f = torch.rand(R, Kf - Kfd, **f32) if draw else noise_in["u_fine"].to(**f32).contiguous()
+            u_j = torch.rand(R, Kf - Kfd, **f32) if draw else noise_in["u_fine_jit"].to(**f32).contiguous()
+            noise.u_fine, noise.u_fine_jit = pn.dptr(u_f), pn.dptr(u_j)
+            keep += [u_f, u_j]
+        if fine and Kfd > 0:
+            n_d = torch.randn(R, Kfd, **f32) if draw else noise_in["n_depth"].to(**f32).contiguous()
+            noise.n_depth = pn.dptr(n_d)
+            keep.append(n_d)
+
+        scene, mc, mf, keep2 = model._scene_struct(want_fine=fine)
+        if scene.SB != SB:
+            raise RuntimeError(f"rays have {SB} objects but encode() saw {scene.SB}")
+        cfg = pn.PnrRenderCfg(Kc, Kf, Kfd, float(self.depth_std), 1 if self.white_bkgd else 0,
+                              pn.ENGINES[model.engine])
+        out = pn.PnrRenderOut()
+        res = DotMap()
+        rgb_c, dep_c = torch.empty(R, 3, **f32), torch.empty(R, **f32)
+        out.rgb_coarse, out.depth_coarse = pn.dptr(rgb_c), pn.dptr(dep_c)
+        res.coarse = DotMap(rgb=rgb_c.view(SB, B, 3), depth=dep_c.view(SB, B))
+        if want_weights:
+            w_c = torch.empty(R, Kc, **f32)
+            out.weights_coarse = pn.dptr(w_c)
+            res.coarse.weights = w_c.view(SB, B, Kc)
+        if want_z:
+            z_c = torch.empty(R, Kc, **f32)
+            out.z_coarse = pn.dptr(z_c)
+            res.coarse.z = z_c.view(SB, B, Kc)
+        if fine:
+            rgb_f, dep_f = torch.empty(R, 3, **f32), torch.empty(R, **f32)
+            out.rgb_fine, out.depth_fine = pn.dptr(rgb_f), pn.dptr(dep_f)
+            res.fine = DotMap(rgb=rgb_f.view(SB, B, 3), depth=dep_f.view(SB, B))
+            if want_weights:
+                w_f = torch.empty(R, Kc + Kf, **f32)
+                out.weights_fine = pn.dptr(w_f)
+                res.fine.weights = w_f.view(SB, B, Kc + Kf)
+            if want_z:
+                z_f = torch.empty(R, Kc + Kf, **f32)
+                out.z_fine = pn.dptr(z_f)
+                res.fine.z = z_f.view(SB, B, Kc + Kf)
+        L = pn.lib()
+        nbytes = L.pnr_render_workspace_bytes(scene, mc, mf, cfg, B)
+        ws = pn.workspace(dev, nbytes)
+        with torch.cuda.device(dev):
+            pn.check(L.pnr_render(scene, mc, mf, cfg, pn.dptr(rays_c, "rays"), noise, out, B, ws.data_ptr(),
+                                  ws.numel(), pn.stream_ptr(dev)))
+        return res
+
+    def _format_outputs(self, rendered, sb, want_weights=False):
+        w, rgb, depth = rendered
+        if sb > 0:
+            rgb, depth, w = rgb.reshape(sb, -1, 3), depth.reshape(sb, -1), w.reshape(sb, -1, w.shape[-1])
+        d = DotMap(rgb=rgb, depth=depth)
+        if want_weights:
+            d.weights = w
+        return d
+
+    def sched_step(self, steps=1):
+        """Advance the sample-count schedule (nerf.py:318-338)."""
+        if self.sched is None:
+            return
+        self.iter_idx += steps
+        while (self.last_sched.item() < len(self.sched[0])
+               and self.iter_idx.item() >= self.sched[0][self.last_sched.item()]):
+            self.n_coarse = self.sched[1][self.last_sched.item()]
+            self.n_fine = self.sched[2][self.last_sched.item()]
+            print("INFO: NeRF sampling resolution changed on schedule ==> c", self.n_coarse, "f", self.n_fine)
+            self.last_sched += 1
+
+    @classmethod
+    def from_conf(cls, conf, white_bkgd=False, lindisp=False, eval_batch_size=100000):
+        return cls(conf.get_int("n_coarse", 128), conf.get_int("n_fine", 0),
+                   n_fine_depth=conf.get_int("n_fine_depth", 0), noise_std=conf.get_float("noise_std", 0.0),
+                   depth_std=conf.get_float("depth_std", 0.01), white_bkgd=conf.get_float("white_bkgd", white_bkgd),
+                   lindisp=lindisp, eval_batch_size=conf.get_int("eval_batch_size", eval_batch_size),
+                   sched=conf.get_list("sched", None))
+
+    def bind_parallel(self, net, gpus=None, simple_output=False):
+        """Returns a module: forward(rays (SB,B,8), want_weights) -> (rgb, depth) or nested dict."""
+        wrapped = _RenderWrapper(net, self, simple_output=simple_output)
+        if gpus is not None and len(gpus) > 1:
+            print("Using multi-GPU", gpus)
+            wrapped = _ShardedRender(wrapped, gpus)
+        return wrapped
