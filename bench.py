@@ -259,7 +259,7 @@ def cpu_reference_run(cfg, sample_rays, reps):
     """Reference algorithm on the host cores: oracle/pnr_oracle.py (torch CPU port that mirrors
     the reference's op structure incl. its point-chunk loop), all threads."""
     oracle = _load("pnr_oracle", os.path.join(ROOT, "oracle", "pnr_oracle.py"))
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(os.cpu_count(), 32))  # more threads than this only adds sync overhead here
     src, _, focal, c = synth.make_cameras(cfg)
     Hl, Wl = cfg["H"] // 2, cfg["W"] // 2
     latent = synth.make_latent(5, cfg["NS"], Hl, Wl)

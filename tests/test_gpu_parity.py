@@ -66,24 +66,28 @@ def test_stage_entry_points():
     R, Kc, Kf, Kfd = rays.shape[0], cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"]
     L = pn.lib()
     sp = pn.stream_ptr(dev)
+    d = lambda t: t.to(dev).contiguous()  # keep every device tensor alive until the sync below
+    n = case["noise"]
+    u_c, zc_ref, wc_ref, dc_ref = d(n["u_coarse"]), d(ref["coarse"]["z"]), d(ref["coarse"]["weights"]), d(ref["coarse"]["depth"])
+    u_f, u_j, n_d = d(n["u_fine"]), d(n["u_fine_jit"]), d(n["n_depth"])
     z = torch.empty(R, Kc, device=dev)
-    pn.check(L.pnr_sample_coarse(pn.dptr(rays), None, pn.dptr(case["noise"]["u_coarse"].to(dev)), pn.dptr(z), R, Kc, sp))
+    pn.check(L.pnr_sample_coarse(pn.dptr(rays), None, pn.dptr(u_c), pn.dptr(z), R, Kc, sp))
     assert (z.cpu() - ref["coarse"]["z"]).abs().max() < 1e-6
     # composite on the oracle's field values
     st = gu.oracle_state(case)
-    pts = case["rays"].reshape(-1, 8)[:, None, :3] + ref["coarse"]["z"].unsqueeze(2) * case["rays"].reshape(-1, 8)[:, None, 3:6]
-    dirs = case["rays"].reshape(-1, 8)[:, None, 3:6].expand(-1, Kc, -1)
+    r8 = case["rays"].reshape(-1, 8)
+    pts = r8[:, None, :3] + ref["coarse"]["z"].unsqueeze(2) * r8[:, None, 3:6]
+    dirs = r8[:, None, 3:6].expand(-1, Kc, -1)
     field = gu.oracle.field_eval(pts.reshape(1, -1, 3), dirs.reshape(1, -1, 3), st, case["latent"], case["wc"], cfg["NS"])
-    field = field.reshape(R, Kc, 4).to(dev).contiguous()
+    field = d(field.reshape(R, Kc, 4))
     w = torch.empty(R, Kc, device=dev); rgb = torch.empty(R, 3, device=dev); dep = torch.empty(R, device=dev)
-    pn.check(L.pnr_composite(pn.dptr(rays), pn.dptr(ref["coarse"]["z"].to(dev)), pn.dptr(field), 1, pn.dptr(w), pn.dptr(rgb), pn.dptr(dep), R, Kc, sp))
+    pn.check(L.pnr_composite(pn.dptr(rays), pn.dptr(zc_ref), pn.dptr(field), 1, pn.dptr(w), pn.dptr(rgb), pn.dptr(dep), R, Kc, sp))
     assert (w.cpu() - ref["coarse"]["weights"]).abs().max() < 1e-6
     assert (rgb.cpu() - ref["coarse"]["rgb"]).abs().max() < 1e-5
     zf = torch.empty(R, Kc + Kf, device=dev)
-    n = case["noise"]
-    pn.check(L.pnr_sample_fine(pn.dptr(rays), pn.dptr(ref["coarse"]["z"].to(dev)), pn.dptr(ref["coarse"]["weights"].to(dev)),
-                               pn.dptr(ref["coarse"]["depth"].to(dev)), pn.dptr(n["u_fine"].to(dev)), pn.dptr(n["u_fine_jit"].to(dev)),
-                               pn.dptr(n["n_depth"].to(dev)), 0.01, pn.dptr(zf), R, Kc, Kf, Kfd, sp))
+    pn.check(L.pnr_sample_fine(pn.dptr(rays), pn.dptr(zc_ref), pn.dptr(wc_ref), pn.dptr(dc_ref), pn.dptr(u_f), pn.dptr(u_j),
+                               pn.dptr(n_d), 0.01, pn.dptr(zf), R, Kc, Kf, Kfd, sp))
+    torch.cuda.synchronize()
     flipped = _flipped_rays(zf.cpu(), ref["fine"]["z"])
     assert flipped.float().mean() <= 0.03
     assert (zf.cpu()[~flipped] - ref["fine"]["z"][~flipped]).abs().max() < 1e-5
