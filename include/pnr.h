@@ -181,6 +181,10 @@ int64_t pnr_launch_count(void);
 int pnr_profile_begin(void);
 int pnr_profile_end(double* total_ms, int64_t* launches);
 
+/* Debug / test hook for the tensor engine: synchronises the current device and returns its
+ * status word (0 = ok, otherwise the tag of the first barrier wait that timed out), then clears it. */
+int pnr_tc_status(int* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,7 +96,7 @@ k_sgemm_nt(const float* __restrict__ A, int lda, const float* __restrict__ W, co
   }
 }
 
-static int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N,
+int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N,
                  int K, bool relu_a, bool accum, cudaStream_t s) {
   if (M == 0) return PNR_OK;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);

@@ -1,25 +1,834 @@
-// Tensor engine (tcgen05) -- placeholder until the fused kernel lands; reports "unsupported".
+// Tensor engine: the conditioned MLP of pixelNeRF (ResnetFC d=512, 5 blocks, views averaged
+// before block 3; src/model/resnetfc.py:132-184) fused with point geometry, the latent gather,
+// the multi-view mean and the output activations (src/model/models.py:158-265) in ONE
+// persistent sm_100a kernel.  No [rows x 512] activation ever leaves the SM.
+//
+// Design (DESIGN.md "tensor engine"):
+//  * A CTA PAIR (cluster of 2, tcgen05 cta_group::2, UMMA M=128 N=256 K=16) owns a tile of
+//    128 points (64 per CTA).  Per view it runs lin_in + 3 ResNet blocks on the (point, view)
+//    rows, sums the views through a per-thread-private scratch line, then runs blocks 3-4 and
+//    lin_out on the averaged rows.
+//  * TMEM (512 columns) holds the two fp32 accumulators of a 64 x 512 row tile in the 2-CTA
+//    "2x2" layout: X (residual stream) in columns [0,256), H (hidden) in [256,512).
+//  * Operands are error-compensated fp16 pairs: A = Ahi + Alo, W = Whi + Wlo (both splits exact
+//    to ~2^-22), D += Ahi*Whi + Alo*Whi + Ahi*Wlo with fp32 accumulation -- 3 tensor passes per
+//    algorithmic GEMM, the cheapest split that meets the 1e-4 RGB tolerance.
+//    Weights are pre-scaled by a power of two (exact) so their low parts stay normal in fp16.
+//  * lin_z[i](latent) is NOT a per-sample GEMM: bilinear interpolation commutes with a linear
+//    layer, so pnr_project_latent builds P_i = lin_z[i](latent) (+ biases) once per encode()
+//    and the epilogue gathers 4 taps of P_i and adds them to the residual stream.
+//  * Warp roles per CTA: 8 worker warps (TMEM -> registers -> fp16 hi/lo -> 128B-swizzled smem A
+//    tiles, gathers, output), 1 MMA-issue warp (leader CTA; forwards barriers in the peer),
+//    1 weight-stream warp (cp.async.bulk of pre-swizzled 16 KB weight tiles, 5-slot ring).
+#include <cuda_fp16.h>
+
 #include "pnr_common.cuh"
+#include "pnr_geom.cuh"
 
 namespace pnr {
-bool tc_supported(const PnrScene&, const PnrMlp&) { return false; }
-size_t tc_workspace_bytes(const PnrScene&, const PnrMlp&, int64_t) { return 0; }
-int tc_field_eval(const PnrScene&, const PnrMlp&, const float*, const PointSource&, int64_t, float*, void*, size_t,
-                  cudaStream_t) {
-  set_error("tensor engine not built");
-  return PNR_ERR_UNSUPPORTED;
+
+int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
+          bool relu_a, bool accum, cudaStream_t s);  // pnr_field_simt.cu
+
+namespace tc {
+
+constexpr int D = 512;
+constexpr int ROWS = 64;                 // rows (points) per CTA
+constexpr int TILE_POINTS = 128;         // per CTA pair
+constexpr int NWORKERS = 256;            // 8 worker warps
+constexpr int WARP_MMA = 8;
+constexpr int WARP_LOAD = 9;
+constexpr int NTHREADS = 320;
+constexpr int SLOT_BYTES = 16384;        // 128 weight rows x 64 k x fp16
+constexpr int NSLOTS = 5;
+constexpr int A_CHUNK_BYTES = 16384;     // 64 rows x 64 k x fp16, hi then lo
+constexpr int A_BYTES = 8 * A_CHUNK_BYTES;
+constexpr int SLOTS_LIN_IN = 4;
+constexpr int SLOTS_FC = 32;
+constexpr int SLOTS_PER_RANK = SLOTS_LIN_IN + 10 * SLOTS_FC;  // 324
+constexpr int HEADER_BYTES = 256;
+constexpr uint32_t X_COL = 0, H_COL = 256;
+
+// shared memory map (offsets from the 1024-aligned base)
+constexpr int SM_A = 0;
+constexpr int SM_B = SM_A + A_BYTES;                    // 131072
+constexpr int SM_GEO = SM_B + NSLOTS * SLOT_BYTES;      // 212992: [64][8] words
+constexpr int SM_PART = SM_GEO + ROWS * 8 * 4;          // 215040: [64][4][4] floats
+constexpr int SM_BAR = SM_PART + ROWS * 16 * 4;         // 219136
+constexpr int SM_TOTAL = SM_BAR + 512;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;             // + alignment slack
+
+// barrier indices (8 bytes each)
+constexpr int BAR_B_FULL = 0;                 // [NSLOTS]
+constexpr int BAR_B_PEER = BAR_B_FULL + NSLOTS;   // [NSLOTS] (leader only)
+constexpr int BAR_B_EMPTY = BAR_B_PEER + NSLOTS;  // [NSLOTS]
+constexpr int BAR_A_FULL = BAR_B_EMPTY + NSLOTS;  // [8]
+constexpr int BAR_F_FULL = BAR_A_FULL + 8;
+constexpr int BAR_ACC = BAR_F_FULL + 1;
+constexpr int BAR_COUNT = BAR_ACC + 1;
+constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
+
+constexpr long long TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: turns a protocol bug into an error, not a hang
+
+struct Params {
+  PnrScene sc;
+  PointSource src;
+  PnrMlp mlp;
+  const uint8_t* packed;
+  const float* proj;      // [3][V][Hl][Wl][512]
+  float* scratch;         // [gridDim.x][512][64]
+  float* out;             // [total_points][4]
+  int64_t total_points;
+  int64_t n_tiles;
+  int* status;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {  // barrier of CTA `cta` of the pair
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int tag) {
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*(volatile int*)status != 0) return;  // another thread already failed: drain
+    if (clock64() - t0 > TIMEOUT_CYCLES) {
+      atomicCAS(status, 0, tag);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, status, tag);
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues for the CTA pair.
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs complete -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+// kind::f16, A/B = F16 K-major, D = F32, M = 128 (64 rows per CTA), N = 256
+constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t split_pack(float a0, float a1, uint32_t& lo_out) {
+  a0 = fminf(a0, 65504.f);
+  a1 = fminf(a1, 65504.f);
+  __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+  __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+  lo_out = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  return (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+}
+
+// relu(y[0..15]) -> fp16 hi/lo -> swizzled A tile (row m, k columns [16g, 16g+16) of chunk at `chunk`)
+__device__ __forceinline__ void store_a16(uint8_t* chunk, int m, int g, const float* y) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) hi[e] = split_pack(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f), lo[e]);
+  uint8_t* row_hi = chunk + m * 128;
+  uint8_t* row_lo = row_hi + 8192;
+  const int u0 = (2 * g) ^ (m & 7), u1 = (2 * g + 1) ^ (m & 7);
+  *reinterpret_cast<uint4*>(row_hi + u0 * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(row_hi + u1 * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  *reinterpret_cast<uint4*>(row_lo + u0 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(row_lo + u1 * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+enum { MODE_GATHER = 0, MODE_BIAS_WB = 1, MODE_HIDDEN = 2, MODE_COMBINE = 3, MODE_OUT = 4 };
+
+struct WorkerCtx {
+  uint8_t* smem;
+  uint32_t tmem;        // base tmem address incl. this warp's lane quarter
+  uint32_t bar_base;    // smem address of the barrier array
+  int rank;             // CTA rank in the pair
+  int warp, lane, q, s, m, n_hi;
+  float w_scale, w_inv;
+  int* status;
+};
+
+// One epilogue pass over this thread's 128 columns (two runs of 64: MMA blocks b = 0, 1).
+//   acc_col  : TMEM column base of the accumulator read (X_COL or H_COL)
+//   bias     : per-feature vector added (MODE_BIAS_WB / HIDDEN / COMBINE / OUT)
+//   proj_i   : projected-latent map gathered (MODE_GATHER)
+template <int MODE>
+__device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
+                                         const float* __restrict__ bias, const float* __restrict__ proj_i,
+                                         int view, float* __restrict__ scratch, float* out_part) {
+  const uint32_t* geo = reinterpret_cast<const uint32_t*>(c.smem + SM_GEO) + c.m * 8;
+  uint32_t off[4];
+  float wt[4];
+  if (MODE == MODE_GATHER) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      off[k] = geo[k];
+      wt[k] = __uint_as_float(geo[4 + k]);
+    }
+  }
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  const int NS = p.sc.NS;
+#pragma unroll 1
+  for (int b = 0; b < 2; ++b) {
+    const int nb = b * 256 + c.n_hi * 128 + c.s * 64;  // first feature of this run
+    const int j = nb >> 6;                            // k-chunk of the next layer this run feeds
+    uint8_t* chunk = c.smem + SM_A + j * A_CHUNK_BYTES;
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      const int n0 = nb + g * 16;
+      const uint32_t taddr = c.tmem + acc_col + b * 128 + c.s * 64 + g * 16;
+      float y[16];
+      if (MODE == MODE_GATHER) {
+        float4 t[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            t[k][cc] = __ldg(reinterpret_cast<const float4*>(proj_i + off[k] + n0) + cc);
+        tmem_ld16(taddr, y);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          y[4 * cc + 0] = y[4 * cc + 0] * c.w_inv + (((t[0][cc].x * wt[0] + t[1][cc].x * wt[1]) + t[2][cc].x * wt[2]) + t[3][cc].x * wt[3]);
+          y[4 * cc + 1] = y[4 * cc + 1] * c.w_inv + (((t[0][cc].y * wt[0] + t[1][cc].y * wt[1]) + t[2][cc].y * wt[2]) + t[3][cc].y * wt[3]);
+          y[4 * cc + 2] = y[4 * cc + 2] * c.w_inv + (((t[0][cc].z * wt[0] + t[1][cc].z * wt[1]) + t[2][cc].z * wt[2]) + t[3][cc].z * wt[3]);
+          y[4 * cc + 3] = y[4 * cc + 3] * c.w_inv + (((t[0][cc].w * wt[0] + t[1][cc].w * wt[1]) + t[2][cc].w * wt[2]) + t[3][cc].w * wt[3]);
+        }
+      } else {
+        float4 bv[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) bv[cc] = __ldg(reinterpret_cast<const float4*>(bias + n0) + cc);
+        tmem_ld16(taddr, y);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          y[4 * cc + 0] = y[4 * cc + 0] * c.w_inv + bv[cc].x;
+          y[4 * cc + 1] = y[4 * cc + 1] * c.w_inv + bv[cc].y;
+          y[4 * cc + 2] = y[4 * cc + 2] * c.w_inv + bv[cc].z;
+          y[4 * cc + 3] = y[4 * cc + 3] * c.w_inv + bv[cc].w;
+        }
+      }
+      bool produce = true;
+      if (MODE == MODE_COMBINE) {
+        // multi-view mean (util.combine_interleaved): sum in view order, then divide
+        if (NS > 1) {
+          float* sp = scratch + (size_t)n0 * ROWS + c.m;  // [feature][row]: lanes are contiguous
+          if (view == 0) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sp[e * ROWS] = y[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] = sp[e * ROWS] + y[e];
+            if (view < NS - 1) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) sp[e * ROWS] = y[e];
+            }
+          }
+          if (view == NS - 1) {
+            const float ns = (float)NS;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] = y[e] / ns;
+          }
+        }
+        produce = (view == NS - 1);
+      }
+      if (MODE == MODE_GATHER || MODE == MODE_BIAS_WB || (MODE == MODE_COMBINE && produce)) {
+        float z[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = y[e] * c.w_scale;
+        tmem_st16(c.tmem + X_COL + b * 128 + c.s * 64 + g * 16, z);  // residual stream write-back
+      }
+      if (MODE == MODE_OUT) {
+        // lin_out(relu(x)) partial dot products over this thread's columns (resnetfc.py:183)
+        const float* W = p.mlp.lin_out_w;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float a = fmaxf(y[e], 0.f);
+          o0 = fmaf(a, __ldg(W + 0 * D + n0 + e), o0);
+          o1 = fmaf(a, __ldg(W + 1 * D + n0 + e), o1);
+          o2 = fmaf(a, __ldg(W + 2 * D + n0 + e), o2);
+          o3 = fmaf(a, __ldg(W + 3 * D + n0 + e), o3);
+        }
+      } else if (produce) {
+        store_a16(chunk, c.m, g, y);
+      }
+    }
+    if (MODE != MODE_OUT && !(MODE == MODE_COMBINE && view != NS - 1)) {
+      // publish this warp's half of A chunk j to the tensor core of the pair
+      fence_proxy_async();
+      if (MODE != MODE_HIDDEN) tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
+    }
+  }
+  if (MODE == MODE_OUT) {
+    float4* dst = reinterpret_cast<float4*>(out_part) + c.m * 4 + (c.n_hi * 2 + c.s);
+    *dst = make_float4(o0, o1, o2, o3);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field_tc(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const uint32_t bar_base = smem_u32(smem + SM_BAR);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEM_PTR);
+  const int NS = p.sc.NS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOTS; ++i) {
+      mbar_init(bar_base + (BAR_B_FULL + i) * 8, 1);
+      mbar_init(bar_base + (BAR_B_PEER + i) * 8, 1);
+      mbar_init(bar_base + (BAR_B_EMPTY + i) * 8, 1);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(bar_base + (BAR_A_FULL + i) * 8, 4);   // 2 warps x 2 CTAs
+    mbar_init(bar_base + BAR_F_FULL * 8, 16);                                    // 8 warps x 2 CTAs
+    mbar_init(bar_base + BAR_ACC * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const float w_scale = reinterpret_cast<const float*>(p.packed)[0];
+  const float w_inv = reinterpret_cast<const float*>(p.packed)[1];
+  const uint8_t* slots = p.packed + HEADER_BYTES + (size_t)rank * SLOTS_PER_RANK * SLOT_BYTES;
+  const size_t map_stride = (size_t)p.sc.SB * NS * p.sc.Hl * p.sc.Wl * D;
+
+  if (warp < 8) {
+    // =============================== worker warps ===============================
+    WorkerCtx c;
+    c.smem = smem;
+    c.rank = rank;
+    c.warp = warp;
+    c.lane = lane;
+    c.q = warp & 3;
+    c.s = warp >> 2;
+    c.m = 32 * (c.q & 1) + lane;
+    c.n_hi = c.q >> 1;
+    c.tmem = tmem_base + ((uint32_t)(32 * c.q) << 16);
+    c.bar_base = bar_base;
+    c.w_scale = w_scale;
+    c.w_inv = w_inv;
+    c.status = p.status;
+    float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
+    float* out_part = reinterpret_cast<float*>(smem + SM_PART);
+    const uint32_t acc_bar = bar_base + BAR_ACC * 8;
+    uint32_t acc_phase = 0;
+    const int grow = threadIdx.x & 63;   // row handled in the geometry stage
+    const int gsub = threadIdx.x >> 6;   // which 12 of the 48 input channels
+
+    for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+      int64_t pt = tile * TILE_POINTS + rank * ROWS + grow;
+      if (pt >= p.total_points) pt = p.total_points - 1;
+      const int sb = (int)(pt / p.src.P);
+      float x[3], d[3];
+      load_point(p.src, pt, x, d);
+      for (int v = 0; v < NS; ++v) {
+        // ---- geometry + the 42 input channels -> A chunk 0 (lin_in operand) ----
+        {
+          PointGeom pg = point_geometry(p.sc, sb, v, x, d);
+          if (gsub == 0) {
+            uint32_t* geo = reinterpret_cast<uint32_t*>(smem + SM_GEO) + grow * 8;
+            const uint32_t vbase = (uint32_t)(sb * NS + v) * p.sc.Hl * p.sc.Wl;
+            geo[0] = (vbase + pg.y0 * p.sc.Wl + pg.x0) * D;
+            geo[1] = (vbase + pg.y0 * p.sc.Wl + pg.x1) * D;
+            geo[2] = (vbase + pg.y1 * p.sc.Wl + pg.x0) * D;
+            geo[3] = (vbase + pg.y1 * p.sc.Wl + pg.x1) * D;
+            geo[4] = __float_as_uint(pg.w_nw);
+            geo[5] = __float_as_uint(pg.w_ne);
+            geo[6] = __float_as_uint(pg.w_sw);
+            geo[7] = __float_as_uint(pg.w_se);
+          }
+          uint8_t* row_hi = smem + SM_A + grow * 128;
+          uint8_t* row_lo = row_hi + 8192;
+#pragma unroll 1
+          for (int e = 0; e < 12; e += 2) {
+            const int ch = gsub * 12 + e;
+            uint32_t lo;
+            float f0 = feat_channel(pg, ch), f1 = feat_channel(pg, ch + 1);
+            f0 = fmaxf(fminf(f0, 65504.f), -65504.f);
+            f1 = fmaxf(fminf(f1, 65504.f), -65504.f);
+            __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+            __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
+            uint32_t hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            const int byte = ((ch >> 3) ^ (grow & 7)) * 16 + (ch & 7) * 2;
+            *reinterpret_cast<uint32_t*>(row_hi + byte) = hi;
+            *reinterpret_cast<uint32_t*>(row_lo + byte) = lo;
+          }
+          fence_proxy_async();
+          tc_fence_before();  // this warp's earlier TMEM reads (previous view / tile) precede the next lin_in MMA
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(bar_base + BAR_F_FULL * 8, 0);
+          workers_sync();  // geometry visible to all worker warps
+        }
+        // ---- lin_in done -> blocks 0..2 ----
+        for (int blk = 0; blk < 3; ++blk) {
+          mbar_wait(acc_bar, acc_phase, p.status, 100 + blk);  // X ready (lin_in or fc_1 of blk-1)
+          acc_phase ^= 1;
+          tc_fence_after();
+          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, v, nullptr, nullptr);
+          mbar_wait(acc_bar, acc_phase, p.status, 110 + blk);  // H ready
+          acc_phase ^= 1;
+          tc_fence_after();
+          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr);
+        }
+        mbar_wait(acc_bar, acc_phase, p.status, 120);  // X after fc_1 of block 2
+        acc_phase ^= 1;
+        tc_fence_after();
+        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr);
+      }
+      // ---- blocks 3..4 on the view-averaged rows ----
+      mbar_wait(acc_bar, acc_phase, p.status, 130);
+      acc_phase ^= 1;
+      tc_fence_after();
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr);
+      mbar_wait(acc_bar, acc_phase, p.status, 131);
+      acc_phase ^= 1;
+      tc_fence_after();
+      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr);
+      mbar_wait(acc_bar, acc_phase, p.status, 132);
+      acc_phase ^= 1;
+      tc_fence_after();
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr);
+      mbar_wait(acc_bar, acc_phase, p.status, 133);
+      acc_phase ^= 1;
+      tc_fence_after();
+      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part);
+      tc_fence_before();
+      workers_sync();
+      if (threadIdx.x < ROWS) {
+        const int64_t opt = tile * TILE_POINTS + rank * ROWS + threadIdx.x;
+        if (opt < p.total_points) {
+          const float4* pp = reinterpret_cast<const float4*>(out_part) + threadIdx.x * 4;
+          float4 a = pp[0], b2 = pp[1], c2 = pp[2], d2 = pp[3];
+          const float* bo = p.mlp.lin_out_b;
+          float r0 = ((a.x + b2.x) + c2.x) + d2.x + bo[0];
+          float r1 = ((a.y + b2.y) + c2.y) + d2.y + bo[1];
+          float r2 = ((a.z + b2.z) + c2.z) + d2.z + bo[2];
+          float r3 = ((a.w + b2.w) + c2.w) + d2.w + bo[3];
+          float4 o;
+          o.x = 1.0f / (1.0f + expf(-r0));   // sigmoid rgb, relu sigma (models.py:260-264)
+          o.y = 1.0f / (1.0f + expf(-r1));
+          o.z = 1.0f / (1.0f + expf(-r2));
+          o.w = fmaxf(r3, 0.f);
+          reinterpret_cast<float4*>(p.out)[opt] = o;
+        }
+      }
+      workers_sync();  // out_part is reused by the next tile
+    }
+  } else if (warp == WARP_MMA) {
+    if (lane == 0) {
+      if (rank == 0) {
+        // =============================== MMA issuer (leader CTA) ===============================
+        uint32_t seq = 0;          // weight-slot sequence number
+        uint32_t a_phase = 0, f_phase = 0;
+        const uint32_t a_base = smem_u32(smem + SM_A), b_base = smem_u32(smem + SM_B);
+        auto run_slot = [&](uint32_t dcol, uint32_t a_addr0, uint32_t a_addr1, int ksteps, bool overwrite_first) {
+          // one 16 KB weight slot: D[dcol] += A(a_addr0) * B  (+ A(a_addr1) * B if a_addr1 != 0)
+          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+          mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl);
+          mbar_wait(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl);
+          tc_fence_after();
+          const uint32_t b_addr = b_base + sl * SLOT_BYTES;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_2sm(tmem_base + dcol, make_desc(a_addr0 + 32 * k), make_desc(b_addr + 32 * k), IDESC,
+                         (overwrite_first && k == 0) ? 0u : 1u);
+          if (a_addr1)
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16_2sm(tmem_base + dcol, make_desc(a_addr1 + 32 * k), make_desc(b_addr + 32 * k), IDESC, 1u);
+          umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+          ++seq;
+        };
+        auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
+          for (int j = 0; j < nchunks; ++j) {
+            if (lin_in) {
+              mbar_wait(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220);
+            } else {
+              mbar_wait(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j);
+            }
+            tc_fence_after();
+            const uint32_t a_hi = a_base + j * A_CHUNK_BYTES, a_lo = a_hi + 8192;
+            for (int b = 0; b < 2; ++b) {
+              run_slot(dcol + b * 128, a_hi, a_lo, ksteps, overwrite && j == 0);  // W_hi slot: Ahi*Whi + Alo*Whi
+              run_slot(dcol + b * 128, a_hi, 0, ksteps, false);                   // W_lo slot: Ahi*Wlo
+            }
+          }
+          if (lin_in) f_phase ^= 1; else a_phase ^= 1;
+          umma_commit_pair(bar_base + BAR_ACC * 8);
+        };
+        for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+          for (int v = 0; v < NS; ++v) {
+            run_layer(X_COL, true, 1, 3, true);                 // lin_in (K = 42 -> 48)
+            for (int blk = 0; blk < 3; ++blk) {
+              run_layer(H_COL, true, 8, 4, false);              // fc_0
+              run_layer(X_COL, false, 8, 4, false);             // fc_1 accumulates onto the residual
+            }
+          }
+          for (int blk = 3; blk < 5; ++blk) {
+            run_layer(H_COL, true, 8, 4, false);
+            run_layer(X_COL, false, 8, 4, false);
+          }
+        }
+      } else {
+        // ============ peer CTA: forward "my half of the weight slot landed" to the leader ============
+        uint32_t seq = 0;
+        const uint32_t per_tile = (uint32_t)NS * (SLOTS_LIN_IN + 6 * SLOTS_FC) + 4 * SLOTS_FC;
+        for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+          for (uint32_t i = 0; i < per_tile; ++i) {
+            const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+            mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl);
+            mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
+            ++seq;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== weight streamer ===============================
+    if (lane == 0) {
+      uint32_t seq = 0;
+      const uint32_t b_base = smem_u32(smem + SM_B);
+      auto stream = [&](int first_slot, int count) {
+        for (int i = 0; i < count; ++i) {
+          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+          mbar_wait(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl);
+          const uint32_t full = bar_base + (BAR_B_FULL + sl) * 8;
+          mbar_expect_tx(full, SLOT_BYTES);
+          bulk_g2s(b_base + sl * SLOT_BYTES, slots + (size_t)(first_slot + i) * SLOT_BYTES, SLOT_BYTES, full);
+          ++seq;
+        }
+      };
+      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+        for (int v = 0; v < NS; ++v) stream(0, SLOTS_LIN_IN + 6 * SLOTS_FC);   // lin_in, blocks 0..2
+        stream(SLOTS_LIN_IN + 6 * SLOTS_FC, 4 * SLOTS_FC);                     // blocks 3..4
+      }
+    }
+  }
+
+  // ---- teardown: everyone done with TMEM / peer smem before it is released ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WARP_MMA) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// weight packing: fp32 [512][K] -> fp16 hi/lo, per-rank 16 KB slots in MMA consumption order
+// ---------------------------------------------------------------------------------------
+__global__ void k_absmax(const float* __restrict__ w, int n, unsigned int* out) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void k_pack_header(const unsigned int* absmax_bits, float* header) {
+  float m = __uint_as_float(*absmax_bits);
+  float s = 1.0f;
+  if (m > 0.f && isfinite(m)) {
+    int e = (int)floorf(log2f(16384.0f / m));
+    e = max(0, min(e, 12));
+    s = exp2f((float)e);
+  }
+  header[0] = s;
+  header[1] = 1.0f / s;
+}
+
+// one block per slot: layer-local slot index ls = (j*2 + b)*2 + part
+__global__ void k_pack_layer(const float* __restrict__ W, int K, uint8_t* __restrict__ dst_rank0,
+                             uint8_t* __restrict__ dst_rank1, const float* __restrict__ header) {
+  const int ls = blockIdx.x, rank = blockIdx.y;
+  const int part = ls & 1, b = (ls >> 1) & 1, j = ls >> 2;
+  uint8_t* dst = (rank ? dst_rank1 : dst_rank0) + (size_t)ls * SLOT_BYTES;
+  const float s = header[0];
+  for (int idx = threadIdx.x; idx < 128 * 64; idx += blockDim.x) {
+    const int i = idx >> 6, kk = idx & 63;
+    const int n = b * 256 + rank * 128 + i, k = j * 64 + kk;
+    float w = (k < K) ? W[(size_t)n * K + k] * s : 0.f;
+    __half hi = __float2half_rn(w);
+    __half val = part ? __float2half_rn(w - __half2float(hi)) : hi;
+    const int byte = i * 128 + (((kk >> 3) ^ (i & 7)) * 16) + (kk & 7) * 2;
+    *reinterpret_cast<__half*>(dst + byte) = val;
+  }
+}
+
+__global__ void k_proj_bias(const float* a, const float* b, float* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+static int* g_status[64] = {nullptr};
+
+static int get_status_buffer(int** out) {
+  int dev = 0;
+  PNR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    set_error("device index out of range");
+    return PNR_ERR_INVALID;
+  }
+  if (!g_status[dev]) {
+    PNR_CUDA(cudaMalloc(&g_status[dev], 256));
+    PNR_CUDA(cudaMemset(g_status[dev], 0, 256));
+  }
+  *out = g_status[dev];
+  return PNR_OK;
+}
+
+}  // namespace tc
+
+bool tc_supported(const PnrScene& sc, const PnrMlp& m) {
+  return m.d_hidden == tc::D && m.d_latent == tc::D && sc.C == tc::D && m.d_in == 42 && m.d_out == 4 &&
+         m.n_blocks == 5 && m.combine_layer == 3 && sc.NS >= 1 && sc.NS <= 64;
+}
+
+static int tc_pairs(int64_t n_tiles) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (pairs > n_tiles) pairs = n_tiles;
+  return (int)(pairs < 1 ? 1 : pairs);
+}
+
+size_t tc_workspace_bytes(const PnrScene&, const PnrMlp&, int64_t total_points) {
+  int64_t n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+  return (size_t)tc_pairs(n_tiles) * 2 * tc::D * tc::ROWS * sizeof(float) + 1024;
+}
+
+int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
+                  int64_t total_points, float* out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!tc_supported(sc, mlp) || !mlp.packed || !proj) {
+    set_error("tensor engine: unsupported shape or missing packed weights / projected latent");
+    return PNR_ERR_UNSUPPORTED;
+  }
+  if (mlp.packed_bytes < pnr_pack_mlp_bytes(&mlp)) {
+    set_error("packed weight buffer too small");
+    return PNR_ERR_INVALID;
+  }
+  if (ws_bytes < tc_workspace_bytes(sc, mlp, total_points)) {
+    set_error("workspace too small for the tensor engine");
+    return PNR_ERR_WORKSPACE;
+  }
+  if (total_points == 0) return PNR_OK;
+  tc::Params p;
+  p.sc = sc;
+  p.src = src;
+  p.mlp = mlp;
+  p.packed = static_cast<const uint8_t*>(mlp.packed);
+  p.proj = proj;
+  p.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  p.out = out;
+  p.total_points = total_points;
+  p.n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+  int rc = tc::get_status_buffer(&p.status);
+  if (rc) return rc;
+  const int pairs = tc_pairs(p.n_tiles);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    PNR_CUDA(cudaFuncSetAttribute(tc::k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  prof_before(s);
+  tc::k_field_tc<<<dim3(pairs * 2), dim3(tc::NTHREADS), tc::SMEM_BYTES, s>>>(p);
+  prof_after(s);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
 }  // namespace pnr
 
+using namespace pnr;
+
 extern "C" {
-size_t pnr_pack_mlp_bytes(const PnrMlp*) { return 0; }
-int pnr_pack_mlp(const PnrMlp*, void*, size_t, void*) {
-  pnr::set_error("tensor engine not built");
-  return PNR_ERR_UNSUPPORTED;
+
+size_t pnr_pack_mlp_bytes(const PnrMlp* mlp) {
+  if (!mlp || mlp->d_hidden != tc::D || mlp->d_latent != tc::D || mlp->n_blocks != 5 || mlp->d_in != 42) return 0;
+  return (size_t)tc::HEADER_BYTES + (size_t)2 * tc::SLOTS_PER_RANK * tc::SLOT_BYTES;
 }
-size_t pnr_project_latent_bytes(const PnrScene*, const PnrMlp*) { return 0; }
-int pnr_project_latent(const PnrScene*, const PnrMlp*, float*, size_t, void*, size_t, void*) {
-  pnr::set_error("tensor engine not built");
-  return PNR_ERR_UNSUPPORTED;
+
+int pnr_pack_mlp(const PnrMlp* mlp, void* packed, size_t packed_bytes, void* stream) {
+  PNR_CHECK_ARG(mlp && packed, "NULL pointer");
+  size_t need = pnr_pack_mlp_bytes(mlp);
+  if (need == 0) {
+    set_error("pnr_pack_mlp: the tensor engine needs d_hidden = d_latent = 512, 5 blocks, d_in = 42");
+    return PNR_ERR_UNSUPPORTED;
+  }
+  PNR_CHECK_ARG(packed_bytes >= need, "packed buffer too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  float* header = reinterpret_cast<float*>(base);
+  unsigned int* absmax = reinterpret_cast<unsigned int*>(base + 64);
+  PNR_CUDA(cudaMemsetAsync(base, 0, tc::HEADER_BYTES, s));
+  // global |w| max over every tensor-engine layer (one power-of-two scale for the whole MLP)
+  tc::k_absmax<<<64, 256, 0, s>>>(mlp->lin_in_w, tc::D * mlp->d_in, absmax);
+  PNR_LAUNCH_CHECK();
+  for (int i = 0; i < 5; ++i) {
+    tc::k_absmax<<<64, 256, 0, s>>>(mlp->fc0_w[i], tc::D * tc::D, absmax);
+    PNR_LAUNCH_CHECK();
+    tc::k_absmax<<<64, 256, 0, s>>>(mlp->fc1_w[i], tc::D * tc::D, absmax);
+    PNR_LAUNCH_CHECK();
+  }
+  tc::k_pack_header<<<1, 1, 0, s>>>(absmax, header);
+  PNR_LAUNCH_CHECK();
+  uint8_t* r0 = base + tc::HEADER_BYTES;
+  uint8_t* r1 = r0 + (size_t)tc::SLOTS_PER_RANK * tc::SLOT_BYTES;
+  tc::k_pack_layer<<<dim3(tc::SLOTS_LIN_IN, 2), 256, 0, s>>>(mlp->lin_in_w, mlp->d_in, r0, r1, header);
+  PNR_LAUNCH_CHECK();
+  for (int i = 0; i < 5; ++i) {
+    size_t o0 = (size_t)(tc::SLOTS_LIN_IN + (2 * i) * tc::SLOTS_FC) * tc::SLOT_BYTES;
+    size_t o1 = (size_t)(tc::SLOTS_LIN_IN + (2 * i + 1) * tc::SLOTS_FC) * tc::SLOT_BYTES;
+    tc::k_pack_layer<<<dim3(tc::SLOTS_FC, 2), 256, 0, s>>>(mlp->fc0_w[i], tc::D, r0 + o0, r1 + o0, header);
+    PNR_LAUNCH_CHECK();
+    tc::k_pack_layer<<<dim3(tc::SLOTS_FC, 2), 256, 0, s>>>(mlp->fc1_w[i], tc::D, r0 + o1, r1 + o1, header);
+    PNR_LAUNCH_CHECK();
+  }
+  return PNR_OK;
 }
+
+size_t pnr_project_latent_bytes(const PnrScene* sc, const PnrMlp* mlp) {
+  if (!sc || !mlp || !tc_supported(*sc, *mlp)) return 0;
+  return (size_t)3 * sc->SB * sc->NS * sc->Hl * sc->Wl * tc::D * sizeof(float);
 }
+
+// proj[i] = lin_z[i](latent) + lin_z[i].bias + (i == 0 ? lin_in.bias : blocks[i-1].fc_1.bias)
+int pnr_project_latent(const PnrScene* sc, const PnrMlp* mlp, float* proj, size_t proj_bytes, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  PNR_CHECK_ARG(sc && mlp && proj && workspace, "NULL pointer");
+  size_t need = pnr_project_latent_bytes(sc, mlp);
+  if (need == 0) {
+    set_error("pnr_project_latent: unsupported shape for the tensor engine");
+    return PNR_ERR_UNSUPPORTED;
+  }
+  PNR_CHECK_ARG(proj_bytes >= need, "proj buffer too small");
+  PNR_CHECK_ARG(workspace_bytes >= 3 * tc::D * sizeof(float) + 256, "workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const int64_t rows = (int64_t)sc->SB * sc->NS * sc->Hl * sc->Wl;
+  for (int i = 0; i < 3; ++i) {
+    const float* extra = (i == 0) ? mlp->lin_in_b : mlp->fc1_b[i - 1];
+    tc::k_proj_bias<<<2, 256, 0, s>>>(mlp->lin_z_b[i], extra, bias + i * tc::D, tc::D);
+    PNR_LAUNCH_CHECK();
+    int rc = sgemm(sc->latent_nhwc, tc::D, mlp->lin_z_w[i], bias + i * tc::D, proj + (size_t)i * rows * tc::D, tc::D,
+                   (int)rows, tc::D, tc::D, false, false, s);
+    if (rc) return rc;
+  }
+  return PNR_OK;
+}
+
+// Debug / test hook: synchronises the device and returns the tensor-engine status word
+// (0 = ok, otherwise the tag of the first barrier wait that timed out); clears it.
+int pnr_tc_status(int* out) {
+  int* buf = nullptr;
+  int rc = tc::get_status_buffer(&buf);
+  if (rc) return rc;
+  PNR_CUDA(cudaDeviceSynchronize());
+  int v = 0;
+  PNR_CUDA(cudaMemcpy(&v, buf, sizeof(int), cudaMemcpyDeviceToHost));
+  PNR_CUDA(cudaMemset(buf, 0, sizeof(int)));
+  if (out) *out = v;
+  return PNR_OK;
+}
+
+}  // extern "C"

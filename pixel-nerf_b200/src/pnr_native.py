@@ -90,6 +90,8 @@ def lib():
     L.pnr_project_latent_bytes.restype = sz
     L.pnr_project_latent.argtypes = [P(PnrScene), P(PnrMlp), vp, sz, vp, sz, vp]
     L.pnr_profile_begin.restype = C.c_int
+    L.pnr_tc_status.argtypes = [P(C.c_int)]
+    L.pnr_tc_status.restype = C.c_int
     L.pnr_profile_end.argtypes = [P(C.c_double), P(C.c_int64)]
     L.pnr_profile_end.restype = C.c_int
     for name in ("pnr_pack_latent", "pnr_sample_coarse", "pnr_composite", "pnr_sample_fine",
@@ -130,6 +132,13 @@ def profile_end():
     ms, n = C.c_double(0.0), C.c_int64(0)
     check(lib().pnr_profile_end(C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+
+def tc_status():
+    """Synchronise and return the tensor engine's status word (0 = ok)."""
+    v = C.c_int(0)
+    check(lib().pnr_tc_status(C.byref(v)))
+    return v.value
 
 
 def launch_count():
