@@ -1,0 +1,137 @@
+"""Host-side logic on CPU: HOCON reader, conf files, model/renderer construction, state_dict
+compatibility, unsupported-flag errors, schedule, DotMap, no-CPU-fallback guard."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pixel-nerf_b200")
+sys.path.insert(0, os.path.join(PKG, "src"))
+
+from util import hocon  # noqa: E402
+import golden_util as gu  # noqa: E402
+import gpu_util  # noqa: E402
+
+
+def test_hocon_subset():
+    c = hocon.parse_string('''
+      # comment
+      a { b = 1, c = [1, 2.5, x]  // trailing
+          d { e = True } }
+      a.b = 2
+      a { d { f = "s t" } }
+      g : null
+      h = some bare words
+    ''')
+    assert c.get_int("a.b") == 2 and c["a.c"] == [1, 2.5, "x"]
+    assert c.get_bool("a.d.e") is True and c.get_string("a.d.f") == "s t"
+    assert c.get("g") is None and c["h"] == "some bare words"
+    assert "a.d.e" in c and "a.zz" not in c
+    assert c.get_int("missing", 7) == 7
+    with pytest.raises(KeyError):
+        c.get_int("missing")
+
+
+@pytest.mark.parametrize("name", ["srn", "sn64", "dtu"])
+def test_conf_files_resolve_includes(name):
+    c = hocon.parse_file(os.path.join(PKG, "conf", "exp", name + ".conf"))
+    assert c.get_int("model.mlp_coarse.n_blocks") == 5 and c.get_int("model.mlp_coarse.combine_layer") == 3
+    assert c.get_int("renderer.n_coarse") == 64 and c.get_list("renderer.sched") == []
+    assert c.get_float("renderer.white_bkgd") == (0.0 if name == "dtu" else 1.0)
+    assert c.get_bool("model.encoder.use_first_pool", True) == (name != "sn64")
+
+
+def test_model_state_dict_keys_and_shapes():
+    case = gu.load_case("tiny")
+    net = gpu_util.build_net(case, device="cpu", engine="simt")
+    sd = net.state_dict()
+    for k in ("code._freqs", "code._phases", "mlp_coarse.lin_in.weight", "mlp_coarse.lin_z.2.bias",
+              "mlp_coarse.blocks.4.fc_1.weight", "mlp_fine.lin_out.bias", "encoder.model.conv1.weight"):
+        assert k in sd, k
+    assert sd["mlp_coarse.lin_in.weight"].shape == (32, 42)
+    assert not any(k.startswith(("poses", "focal", "image_shape")) for k in sd)  # non-persistent buffers
+    assert net.d_in == 42 and net.d_latent == 512 and net.use_viewdirs
+
+
+def test_reference_init_zeroes_fc1():
+    from model.resnetfc import ResnetFC
+    m = ResnetFC(42, d_latent=512, d_hidden=64, combine_layer=3)
+    assert all(float(b.fc_1.weight.abs().sum()) == 0.0 for b in m.blocks)
+    assert len(m.lin_z) == 3
+
+
+def test_unsupported_flags_raise_by_name():
+    from model import make_model
+    conf = gpu_util.model_conf(32)
+    conf.put("use_code_viewdirs", True)
+    with pytest.raises(NotImplementedError, match="use_code_viewdirs"):
+        make_model(conf)
+    conf = gpu_util.model_conf(32)
+    conf.put("mlp_coarse.combine_type", "max")
+    with pytest.raises(NotImplementedError, match="combine_type"):
+        make_model(conf)
+    from render import NeRFRenderer
+    with pytest.raises(NotImplementedError, match="lindisp"):
+        NeRFRenderer(lindisp=True)
+
+
+def test_renderer_conf_schedule_and_state():
+    from render import NeRFRenderer
+    conf = hocon.from_dict(dict(n_coarse=8, n_fine=4, n_fine_depth=2, white_bkgd=True, sched=[[2, 4], [16, 32], [8, 16]]))
+    r = NeRFRenderer.from_conf(conf, eval_batch_size=123)
+    assert (r.n_coarse, r.n_fine, r.n_fine_depth, r.eval_batch_size, r.using_fine) == (8, 4, 2, 123, True)
+    assert r.white_bkgd == 1.0 and set(r.state_dict().keys()) == {"iter_idx", "last_sched"}
+    r.sched_step(2)
+    assert (r.n_coarse, r.n_fine, int(r.last_sched)) == (16, 8, 1)
+    r.sched_step(2)
+    assert (r.n_coarse, r.n_fine, int(r.last_sched)) == (32, 16, 2)
+
+
+def test_no_cpu_fallback_in_inference():
+    case = gu.load_case("tiny")
+    net = gpu_util.build_net(case, device="cpu", engine="simt")
+    renderer = gpu_util.build_renderer(case)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            net(case["ref"]["field_xyz"], coarse=True, viewdirs=case["ref"]["field_dirs"])
+        with pytest.raises(RuntimeError, match="CUDA"):
+            renderer(net, case["rays"])
+
+
+def test_autograd_path_matches_reference_goldens():
+    """The documented grad-mode (training) path: composed torch ops, seeded like the reference."""
+    case = gu.load_case("tiny")
+    net = gpu_util.build_net(case, device="cpu", engine="simt")
+    renderer = gpu_util.build_renderer(case)
+    torch.manual_seed(case["seed"] + 4)
+    out = renderer(net, case["rays"], want_weights=True)
+    assert (out.fine.rgb - case["ref"]["fine_rgb"]).abs().max() < 1e-6
+    out.fine.rgb.sum().backward()
+    assert net.mlp_fine.lin_in.weight.grad is not None
+
+
+def test_dotmap_compat():
+    from render.dotmap_compat import DotMap
+    d = DotMap(coarse=DotMap(rgb=1))
+    d.fine.depth = 2
+    assert d.coarse.rgb == 1 and d.toDict() == {"coarse": {"rgb": 1}, "fine": {"depth": 2}}
+
+
+def test_parse_args_with_expconf(tmp_path, monkeypatch):
+    from util import args as uargs
+    monkeypatch.chdir(tmp_path)
+    a, conf = uargs.parse_args(argv=["-n", "srn_car", "--gpu_id", "0 1", "-R", "1000"])
+    assert a.conf.endswith("conf/exp/srn.conf") and a.gpu_id == [0, 1] and a.ray_batch_size == 1000
+    assert a.dataset_format == "srn" and conf.get_int("model.mlp_fine.d_hidden") == 512
+
+
+def test_shard_bounds_follow_torch_chunk():
+    from render.sharding import shard_bounds
+    for n in (0, 1, 7, 8, 9, 50000):
+        for w in (1, 2, 3, 8):
+            sizes = [b - a for a, b in shard_bounds(n, w)]
+            ref = [t.shape[0] for t in torch.chunk(torch.zeros(n), w)] if n else []
+            assert [s for s in sizes if s] == ref
+            assert sum(sizes) == n
