@@ -35,10 +35,9 @@ namespace tc {
 constexpr int D = 512;
 constexpr int ROWS = 64;                 // rows (points) per CTA
 constexpr int TILE_POINTS = 128;         // per CTA pair
-constexpr int NWORKERS = 256;            // 8 worker warps
-constexpr int WARP_MMA = 8;
-constexpr int WARP_LOAD = 9;
-constexpr int NTHREADS = 320;
+constexpr int NWORKER_WARPS = 16;
+constexpr int WARP_MMA = NWORKER_WARPS;       // warp 16: MMA issue (leader) / slot forwarder (peer)
+constexpr int NTHREADS = (NWORKER_WARPS + 2) * 32;  // + warp 17: weight streamer
 constexpr int SLOT_BYTES = 16384;        // 128 weight rows x 64 k x fp16
 constexpr int NSLOTS = 5;
 constexpr int A_CHUNK_BYTES = 16384;     // 64 rows x 64 k x fp16, hi then lo
@@ -54,7 +53,7 @@ constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + A_BYTES;                    // 131072
 constexpr int SM_GEO = SM_B + NSLOTS * SLOT_BYTES;      // 212992: [64][8] words
 constexpr int SM_PART = SM_GEO + ROWS * 8 * 4;          // 215040: [64][4][4] floats
-constexpr int SM_BAR = SM_PART + ROWS * 16 * 4;         // 219136
+constexpr int SM_BAR = SM_PART + ROWS * 32 * 4;         // out partials: [64][8][4] floats
 constexpr int SM_TOTAL = SM_BAR + 512;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;             // + alignment slack
 
@@ -144,7 +143,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues for the CTA pair.
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -184,6 +183,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// k-chunks of a layer are produced by the workers in 4 waves (0,2 | 1,3 | 4,6 | 5,7); the MMA consumes in that order
+__device__ __forceinline__ int chunk_order(int jj) { return (jj & 4) | ((jj & 1) << 1) | ((jj >> 1) & 1); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
@@ -228,126 +245,141 @@ struct WorkerCtx {
   uint8_t* smem;
   uint32_t tmem;        // base tmem address incl. this warp's lane quarter
   uint32_t bar_base;    // smem address of the barrier array
-  int rank;             // CTA rank in the pair
-  int warp, lane, q, s, m, n_hi;
+  int lane, s, m, n_hi;
   float w_scale, w_inv;
-  int* status;
 };
 
-// One epilogue pass over this thread's 128 columns (two runs of 64: MMA blocks b = 0, 1).
-//   acc_col  : TMEM column base of the accumulator read (X_COL or H_COL)
-//   bias     : per-feature vector added (MODE_BIAS_WB / HIDDEN / COMBINE / OUT)
-//   proj_i   : projected-latent map gathered (MODE_GATHER)
+// A worker thread owns row m and 8 "steps" of 8 features per layer:
+//   step i -> (b = i>>2 MMA block, c = (i>>1)&1 chunk half, h = i&1): features b*256 + n_hi*128 + c*64 + s*16 + h*8 .. +8
+// i.e. the 16 warps sweep the k-chunks of the next layer in 4 waves (2 chunks per wave), so the MMA warp can
+// start after a quarter of the epilogue.  Chunk j = 4b + 2 n_hi + c, column offset inside the chunk s*16 + h*8.
+__device__ __forceinline__ int step_feature(const WorkerCtx& c, int i) {
+  return (i >> 2) * 256 + c.n_hi * 128 + ((i >> 1) & 1) * 64 + c.s * 16 + (i & 1) * 8;
+}
+__device__ __forceinline__ uint32_t step_tmem_col(const WorkerCtx& c, int i) {
+  return (uint32_t)((i >> 2) * 128 + ((i >> 1) & 1) * 64 + c.s * 16 + (i & 1) * 8);
+}
+
+__device__ __forceinline__ void gather_issue(float4* g, const float* __restrict__ proj_i, const uint32_t* off, int n0) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4* src = reinterpret_cast<const float4*>(proj_i + off[k] + n0);
+    g[2 * k] = __ldg(src);
+    g[2 * k + 1] = __ldg(src + 1);
+  }
+}
+
+// One epilogue pass over this thread's 64 features of one layer.
+//   acc_col : TMEM column base of the accumulator read (X_COL or H_COL)
+//   bias    : per-feature vector added (all modes but GATHER);  proj_i: projected-latent map (GATHER)
 template <int MODE>
 __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
-                                         int view, float* __restrict__ scratch, float* out_part) {
-  const uint32_t* geo = reinterpret_cast<const uint32_t*>(c.smem + SM_GEO) + c.m * 8;
+                                         int view, float* __restrict__ scratch, float* out_part, uint32_t acc_bar,
+                                         uint32_t acc_phase, int tag) {
   uint32_t off[4];
   float wt[4];
+  float4 g[2][8];
   if (MODE == MODE_GATHER) {
+    const uint32_t* geo = reinterpret_cast<const uint32_t*>(c.smem + SM_GEO) + c.m * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       off[k] = geo[k];
       wt[k] = __uint_as_float(geo[4 + k]);
     }
+    gather_issue(g[0], proj_i, off, step_feature(c, 0));  // in flight while the MMA of this layer finishes
   }
+  mbar_wait(acc_bar, acc_phase, p.status, tag);
+  tc_fence_after();
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   const int NS = p.sc.NS;
-#pragma unroll 1
-  for (int b = 0; b < 2; ++b) {
-    const int nb = b * 256 + c.n_hi * 128 + c.s * 64;  // first feature of this run
-    const int j = nb >> 6;                            // k-chunk of the next layer this run feeds
-    uint8_t* chunk = c.smem + SM_A + j * A_CHUNK_BYTES;
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-      const int n0 = nb + g * 16;
-      const uint32_t taddr = c.tmem + acc_col + b * 128 + c.s * 64 + g * 16;
-      float y[16];
-      if (MODE == MODE_GATHER) {
-        float4 t[4][4];
+  const bool produce = (MODE != MODE_OUT) && !(MODE == MODE_COMBINE && view != NS - 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+  for (int i = 0; i < 8; ++i) {
+    const int n0 = step_feature(c, i);
+    const uint32_t col = step_tmem_col(c, i);
+    float y[8];
+    if (MODE == MODE_GATHER) {
+      if (i + 1 < 8) gather_issue(g[(i + 1) & 1], proj_i, off, step_feature(c, i + 1));
+      tmem_ld8(c.tmem + acc_col + col, y);
+      const float4* t = g[i & 1];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            t[k][cc] = __ldg(reinterpret_cast<const float4*>(proj_i + off[k] + n0) + cc);
-        tmem_ld16(taddr, y);
+      for (int hh = 0; hh < 2; ++hh) {
+        y[4 * hh + 0] = y[4 * hh + 0] * c.w_inv + (((t[0 + hh].x * wt[0] + t[2 + hh].x * wt[1]) + t[4 + hh].x * wt[2]) + t[6 + hh].x * wt[3]);
+        y[4 * hh + 1] = y[4 * hh + 1] * c.w_inv + (((t[0 + hh].y * wt[0] + t[2 + hh].y * wt[1]) + t[4 + hh].y * wt[2]) + t[6 + hh].y * wt[3]);
+        y[4 * hh + 2] = y[4 * hh + 2] * c.w_inv + (((t[0 + hh].z * wt[0] + t[2 + hh].z * wt[1]) + t[4 + hh].z * wt[2]) + t[6 + hh].z * wt[3]);
+        y[4 * hh + 3] = y[4 * hh + 3] * c.w_inv + (((t[0 + hh].w * wt[0] + t[2 + hh].w * wt[1]) + t[4 + hh].w * wt[2]) + t[6 + hh].w * wt[3]);
+      }
+    } else {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+      tmem_ld8(c.tmem + acc_col + col, y);
+      y[0] = y[0] * c.w_inv + b0.x; y[1] = y[1] * c.w_inv + b0.y; y[2] = y[2] * c.w_inv + b0.z; y[3] = y[3] * c.w_inv + b0.w;
+      y[4] = y[4] * c.w_inv + b1.x; y[5] = y[5] * c.w_inv + b1.y; y[6] = y[6] * c.w_inv + b1.z; y[7] = y[7] * c.w_inv + b1.w;
+    }
+    if (MODE == MODE_COMBINE && NS > 1) {
+      // multi-view mean (util.combine_interleaved): sum in view order, then divide
+      float* sp = scratch + (size_t)n0 * ROWS + c.m;  // [feature][row]: lanes are contiguous
+      if (view == 0) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          y[4 * cc + 0] = y[4 * cc + 0] * c.w_inv + (((t[0][cc].x * wt[0] + t[1][cc].x * wt[1]) + t[2][cc].x * wt[2]) + t[3][cc].x * wt[3]);
-          y[4 * cc + 1] = y[4 * cc + 1] * c.w_inv + (((t[0][cc].y * wt[0] + t[1][cc].y * wt[1]) + t[2][cc].y * wt[2]) + t[3][cc].y * wt[3]);
-          y[4 * cc + 2] = y[4 * cc + 2] * c.w_inv + (((t[0][cc].z * wt[0] + t[1][cc].z * wt[1]) + t[2][cc].z * wt[2]) + t[3][cc].z * wt[3]);
-          y[4 * cc + 3] = y[4 * cc + 3] * c.w_inv + (((t[0][cc].w * wt[0] + t[1][cc].w * wt[1]) + t[2][cc].w * wt[2]) + t[3][cc].w * wt[3]);
-        }
+        for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
       } else {
-        float4 bv[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) bv[cc] = __ldg(reinterpret_cast<const float4*>(bias + n0) + cc);
-        tmem_ld16(taddr, y);
+        for (int e = 0; e < 8; ++e) y[e] = sp[e * ROWS] + y[e];
+        if (view < NS - 1) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          y[4 * cc + 0] = y[4 * cc + 0] * c.w_inv + bv[cc].x;
-          y[4 * cc + 1] = y[4 * cc + 1] * c.w_inv + bv[cc].y;
-          y[4 * cc + 2] = y[4 * cc + 2] * c.w_inv + bv[cc].z;
-          y[4 * cc + 3] = y[4 * cc + 3] * c.w_inv + bv[cc].w;
+          for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
+        } else {
+          const float ns = (float)NS;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] / ns;
         }
-      }
-      bool produce = true;
-      if (MODE == MODE_COMBINE) {
-        // multi-view mean (util.combine_interleaved): sum in view order, then divide
-        if (NS > 1) {
-          float* sp = scratch + (size_t)n0 * ROWS + c.m;  // [feature][row]: lanes are contiguous
-          if (view == 0) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) sp[e * ROWS] = y[e];
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) y[e] = sp[e * ROWS] + y[e];
-            if (view < NS - 1) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) sp[e * ROWS] = y[e];
-            }
-          }
-          if (view == NS - 1) {
-            const float ns = (float)NS;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) y[e] = y[e] / ns;
-          }
-        }
-        produce = (view == NS - 1);
-      }
-      if (MODE == MODE_GATHER || MODE == MODE_BIAS_WB || (MODE == MODE_COMBINE && produce)) {
-        float z[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) z[e] = y[e] * c.w_scale;
-        tmem_st16(c.tmem + X_COL + b * 128 + c.s * 64 + g * 16, z);  // residual stream write-back
-      }
-      if (MODE == MODE_OUT) {
-        // lin_out(relu(x)) partial dot products over this thread's columns (resnetfc.py:183)
-        const float* W = p.mlp.lin_out_w;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float a = fmaxf(y[e], 0.f);
-          o0 = fmaf(a, __ldg(W + 0 * D + n0 + e), o0);
-          o1 = fmaf(a, __ldg(W + 1 * D + n0 + e), o1);
-          o2 = fmaf(a, __ldg(W + 2 * D + n0 + e), o2);
-          o3 = fmaf(a, __ldg(W + 3 * D + n0 + e), o3);
-        }
-      } else if (produce) {
-        store_a16(chunk, c.m, g, y);
       }
     }
-    if (MODE != MODE_OUT && !(MODE == MODE_COMBINE && view != NS - 1)) {
-      // publish this warp's half of A chunk j to the tensor core of the pair
-      fence_proxy_async();
-      if (MODE != MODE_HIDDEN) tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
+    if (MODE == MODE_GATHER || MODE == MODE_BIAS_WB || (MODE == MODE_COMBINE && produce)) {
+      float z[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[e] = y[e] * c.w_scale;
+      tmem_st8(c.tmem + X_COL + col, z);  // residual stream write-back
+    }
+    if (MODE == MODE_OUT) {
+      // lin_out(relu(x)) partial dot products over this thread's features (resnetfc.py:183)
+      const float* W = p.mlp.lin_out_w + n0;
+#pragma unroll
+      for (int e4 = 0; e4 < 2; ++e4) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + 0 * D) + e4);
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + 1 * D) + e4);
+        const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + 2 * D) + e4);
+        const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + 3 * D) + e4);
+        const float a0 = fmaxf(y[4 * e4 + 0], 0.f), a1 = fmaxf(y[4 * e4 + 1], 0.f);
+        const float a2 = fmaxf(y[4 * e4 + 2], 0.f), a3 = fmaxf(y[4 * e4 + 3], 0.f);
+        o0 = fmaf(a3, w0.w, fmaf(a2, w0.z, fmaf(a1, w0.y, fmaf(a0, w0.x, o0))));
+        o1 = fmaf(a3, w1.w, fmaf(a2, w1.z, fmaf(a1, w1.y, fmaf(a0, w1.x, o1))));
+        o2 = fmaf(a3, w2.w, fmaf(a2, w2.z, fmaf(a1, w2.y, fmaf(a0, w2.x, o2))));
+        o3 = fmaf(a3, w3.w, fmaf(a2, w3.z, fmaf(a1, w3.y, fmaf(a0, w3.x, o3))));
+      }
+    } else if (produce) {
+      // relu -> fp16 hi/lo -> one 16-byte unit of the swizzled A tile (row m, unit 2s+h of chunk j)
+      const int j = 4 * (i >> 2) + 2 * c.n_hi + ((i >> 1) & 1);
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hi[e] = split_pack(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f), lo[e]);
+      uint8_t* row_hi = c.smem + SM_A + j * A_CHUNK_BYTES + c.m * 128;
+      const int u = (2 * c.s + (i & 1)) ^ (c.m & 7);
+      *reinterpret_cast<uint4*>(row_hi + u * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row_hi + 8192 + u * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (i & 1) {
+        // this warp's slice of A chunk j is complete: publish it to the tensor core of the pair
+        fence_proxy_async();
+        if (MODE != MODE_HIDDEN) tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
+      }
     }
   }
   if (MODE == MODE_OUT) {
-    float4* dst = reinterpret_cast<float4*>(out_part) + c.m * 4 + (c.n_hi * 2 + c.s);
+    float4* dst = reinterpret_cast<float4*>(out_part) + c.m * 8 + (c.n_hi * 4 + c.s);
     *dst = make_float4(o0, o1, o2, o3);
   }
 }
@@ -369,8 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       mbar_init(bar_base + (BAR_B_PEER + i) * 8, 1);
       mbar_init(bar_base + (BAR_B_EMPTY + i) * 8, 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(bar_base + (BAR_A_FULL + i) * 8, 4);   // 2 warps x 2 CTAs
-    mbar_init(bar_base + BAR_F_FULL * 8, 16);                                    // 8 warps x 2 CTAs
+    for (int i = 0; i < 8; ++i) mbar_init(bar_base + (BAR_A_FULL + i) * 8, 16);  // 8 warps x 2 CTAs per chunk
+    mbar_init(bar_base + BAR_F_FULL * 8, 2 * NWORKER_WARPS);
     mbar_init(bar_base + BAR_ACC * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -391,28 +423,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
   const uint8_t* slots = p.packed + HEADER_BYTES + (size_t)rank * SLOTS_PER_RANK * SLOT_BYTES;
   const size_t map_stride = (size_t)p.sc.SB * NS * p.sc.Hl * p.sc.Wl * D;
 
-  if (warp < 8) {
+  if (warp < NWORKER_WARPS) {
     // =============================== worker warps ===============================
     WorkerCtx c;
     c.smem = smem;
-    c.rank = rank;
-    c.warp = warp;
     c.lane = lane;
-    c.q = warp & 3;
-    c.s = warp >> 2;
-    c.m = 32 * (c.q & 1) + lane;
-    c.n_hi = c.q >> 1;
-    c.tmem = tmem_base + ((uint32_t)(32 * c.q) << 16);
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    c.s = warp >> 2;                 // 0..3: which 16 columns of every chunk
+    c.m = 32 * (q & 1) + lane;       // row of the CTA's 64-row tile
+    c.n_hi = q >> 1;                 // which 128 features of a 256-wide MMA block live in these lanes
+    c.tmem = tmem_base + ((uint32_t)(32 * q) << 16);
     c.bar_base = bar_base;
     c.w_scale = w_scale;
     c.w_inv = w_inv;
-    c.status = p.status;
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
     float* out_part = reinterpret_cast<float*>(smem + SM_PART);
     const uint32_t acc_bar = bar_base + BAR_ACC * 8;
     uint32_t acc_phase = 0;
     const int grow = threadIdx.x & 63;   // row handled in the geometry stage
-    const int gsub = threadIdx.x >> 6;   // which 12 of the 48 input channels
+    const int gsub = threadIdx.x >> 6;   // 0..7: which 6 of the 48 input channels
 
     for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
       int64_t pt = tile * TILE_POINTS + rank * ROWS + grow;
@@ -439,16 +468,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           uint8_t* row_hi = smem + SM_A + grow * 128;
           uint8_t* row_lo = row_hi + 8192;
 #pragma unroll 1
-          for (int e = 0; e < 12; e += 2) {
-            const int ch = gsub * 12 + e;
-            uint32_t lo;
+          for (int e = 0; e < 6; e += 2) {
+            const int ch = gsub * 6 + e;
             float f0 = feat_channel(pg, ch), f1 = feat_channel(pg, ch + 1);
             f0 = fmaxf(fminf(f0, 65504.f), -65504.f);
             f1 = fmaxf(fminf(f1, 65504.f), -65504.f);
             __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
             __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
-            uint32_t hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            const uint32_t hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            const uint32_t lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
             const int byte = ((ch >> 3) ^ (grow & 7)) * 16 + (ch & 7) * 2;
             *reinterpret_cast<uint32_t*>(row_hi + byte) = hi;
             *reinterpret_cast<uint32_t*>(row_lo + byte) = lo;
@@ -459,51 +487,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           if (lane == 0) mbar_arrive_cta(bar_base + BAR_F_FULL * 8, 0);
           workers_sync();  // geometry visible to all worker warps
         }
-        // ---- lin_in done -> blocks 0..2 ----
+        // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
-          mbar_wait(acc_bar, acc_phase, p.status, 100 + blk);  // X ready (lin_in or fc_1 of blk-1)
+          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, v, nullptr, nullptr, acc_bar,
+                                acc_phase, 100 + blk);  // X ready (lin_in or fc_1 of blk-1)
           acc_phase ^= 1;
-          tc_fence_after();
-          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, v, nullptr, nullptr);
-          mbar_wait(acc_bar, acc_phase, p.status, 110 + blk);  // H ready
+          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_bar, acc_phase,
+                                110 + blk);             // H ready
           acc_phase ^= 1;
-          tc_fence_after();
-          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr);
         }
-        mbar_wait(acc_bar, acc_phase, p.status, 120);  // X after fc_1 of block 2
+        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr, acc_bar, acc_phase, 120);
         acc_phase ^= 1;
-        tc_fence_after();
-        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr);
       }
       // ---- blocks 3..4 on the view-averaged rows ----
-      mbar_wait(acc_bar, acc_phase, p.status, 130);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 130);
       acc_phase ^= 1;
-      tc_fence_after();
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr);
-      mbar_wait(acc_bar, acc_phase, p.status, 131);
+      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 131);
       acc_phase ^= 1;
-      tc_fence_after();
-      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr);
-      mbar_wait(acc_bar, acc_phase, p.status, 132);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 132);
       acc_phase ^= 1;
-      tc_fence_after();
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr);
-      mbar_wait(acc_bar, acc_phase, p.status, 133);
+      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part, acc_bar, acc_phase, 133);
       acc_phase ^= 1;
-      tc_fence_after();
-      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part);
       tc_fence_before();
       workers_sync();
       if (threadIdx.x < ROWS) {
         const int64_t opt = tile * TILE_POINTS + rank * ROWS + threadIdx.x;
         if (opt < p.total_points) {
-          const float4* pp = reinterpret_cast<const float4*>(out_part) + threadIdx.x * 4;
-          float4 a = pp[0], b2 = pp[1], c2 = pp[2], d2 = pp[3];
+          const float4* pp = reinterpret_cast<const float4*>(out_part) + threadIdx.x * 8;
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 a = pp[k];
+            r0 += a.x; r1 += a.y; r2 += a.z; r3 += a.w;
+          }
           const float* bo = p.mlp.lin_out_b;
-          float r0 = ((a.x + b2.x) + c2.x) + d2.x + bo[0];
-          float r1 = ((a.y + b2.y) + c2.y) + d2.y + bo[1];
-          float r2 = ((a.z + b2.z) + c2.z) + d2.z + bo[2];
-          float r3 = ((a.w + b2.w) + c2.w) + d2.w + bo[3];
+          r0 += bo[0]; r1 += bo[1]; r2 += bo[2]; r3 += bo[3];
           float4 o;
           o.x = 1.0f / (1.0f + expf(-r0));   // sigmoid rgb, relu sigma (models.py:260-264)
           o.y = 1.0f / (1.0f + expf(-r1));
@@ -538,7 +556,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           ++seq;
         };
         auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
-          for (int j = 0; j < nchunks; ++j) {
+          for (int jj = 0; jj < nchunks; ++jj) {
+            const int j = lin_in ? 0 : chunk_order(jj);
             if (lin_in) {
               mbar_wait(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220);
             } else {
@@ -547,8 +566,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
             tc_fence_after();
             const uint32_t a_hi = a_base + j * A_CHUNK_BYTES, a_lo = a_hi + 8192;
             for (int b = 0; b < 2; ++b) {
-              run_slot(dcol + b * 128, a_hi, a_lo, ksteps, overwrite && j == 0);  // W_hi slot: Ahi*Whi + Alo*Whi
-              run_slot(dcol + b * 128, a_hi, 0, ksteps, false);                   // W_lo slot: Ahi*Wlo
+              run_slot(dcol + b * 128, a_hi, a_lo, ksteps, overwrite && jj == 0);  // W_hi slot: Ahi*Whi + Alo*Whi
+              run_slot(dcol + b * 128, a_hi, 0, ksteps, false);                    // W_lo slot: Ahi*Wlo
             }
           }
           if (lin_in) f_phase ^= 1; else a_phase ^= 1;
@@ -586,19 +605,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     if (lane == 0) {
       uint32_t seq = 0;
       const uint32_t b_base = smem_u32(smem + SM_B);
-      auto stream = [&](int first_slot, int count) {
-        for (int i = 0; i < count; ++i) {
-          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-          mbar_wait(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl);
-          const uint32_t full = bar_base + (BAR_B_FULL + sl) * 8;
-          mbar_expect_tx(full, SLOT_BYTES);
-          bulk_g2s(b_base + sl * SLOT_BYTES, slots + (size_t)(first_slot + i) * SLOT_BYTES, SLOT_BYTES, full);
-          ++seq;
-        }
+      auto stream_slot = [&](int slot_index) {
+        const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+        mbar_wait(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl);
+        const uint32_t full = bar_base + (BAR_B_FULL + sl) * 8;
+        mbar_expect_tx(full, SLOT_BYTES);
+        bulk_g2s(b_base + sl * SLOT_BYTES, slots + (size_t)slot_index * SLOT_BYTES, SLOT_BYTES, full);
+        ++seq;
+      };
+      auto stream_fc = [&](int layer) {  // layer 0..9 = fc_0/fc_1 of blocks 0..4, k-chunks in MMA order
+        const int base = SLOTS_LIN_IN + layer * SLOTS_FC;
+        for (int jj = 0; jj < 8; ++jj)
+          for (int r = 0; r < 4; ++r) stream_slot(base + chunk_order(jj) * 4 + r);
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-        for (int v = 0; v < NS; ++v) stream(0, SLOTS_LIN_IN + 6 * SLOTS_FC);   // lin_in, blocks 0..2
-        stream(SLOTS_LIN_IN + 6 * SLOTS_FC, 4 * SLOTS_FC);                     // blocks 3..4
+        for (int v = 0; v < NS; ++v) {
+          for (int r = 0; r < SLOTS_LIN_IN; ++r) stream_slot(r);
+          for (int l = 0; l < 6; ++l) stream_fc(l);
+        }
+        for (int l = 6; l < 10; ++l) stream_fc(l);
       }
     }
   }
