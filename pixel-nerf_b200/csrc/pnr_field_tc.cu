@@ -91,12 +91,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {  // barrier of CTA `cta` of the pair
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -105,20 +105,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
   return ok;
 }
+// Waits use CTA-scope try_wait (what CUTLASS's ClusterBarrier does): a cluster-scope acquire would make ptxas
+// emit CCTL.IVALL (an L1 invalidate) on every spin.  The data these barriers guard is read by the async proxy
+// (tensor core / TMA), which the producers order with fence.proxy.async before arriving.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int tag) {
   long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (*(volatile int*)status != 0) return;  // another thread already failed: drain
-    if (clock64() - t0 > TIMEOUT_CYCLES) {
-      atomicCAS(status, 0, tag);
-      return;
+    if ((++spins & 0x3FFF) == 0) {  // rarely: has another thread failed / did we time out?
+      if (*(volatile int*)status != 0) return;
+      if (clock64() - t0 > TIMEOUT_CYCLES) {
+        atomicCAS(status, 0, tag);
+        return;
+      }
     }
   }
 }
