@@ -105,10 +105,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: park the warp instead of spinning
       : "memory");
   return ok;
 }
@@ -133,6 +133,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* st
   mbar_wait_slow(bar, parity, status, tag);
 }
 
+// wait and add the stalled cycles to a per-thread counter (debug breakdown, see pnr_tc_counters)
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int* status, int tag, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  mbar_wait_slow(bar, parity, status, tag);
+  acc += clock64() - t0;
+}
+
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -148,6 +156,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -253,6 +266,7 @@ struct WorkerCtx {
   uint32_t bar_base;    // smem address of the barrier array
   int lane, s, m, n_hi;
   float w_scale, w_inv;
+  long long* t_acc;     // cycles spent waiting for the accumulator barrier
 };
 
 // A worker thread owns row m and 8 "steps" of 8 features per layer:
@@ -295,7 +309,7 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
     }
     gather_issue(g[0], proj_i, off, step_feature(c, 0));  // in flight while the MMA of this layer finishes
   }
-  mbar_wait(acc_bar, acc_phase, p.status, tag);
+  mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
   tc_fence_after();
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   const int NS = p.sc.NS;
@@ -442,6 +456,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.bar_base = bar_base;
     c.w_scale = w_scale;
     c.w_inv = w_inv;
+    long long t_acc = 0, t_geo = 0;
+    c.t_acc = &t_acc;
+    const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
     float* out_part = reinterpret_cast<float*>(smem + SM_PART);
     const uint32_t acc_bar = bar_base + BAR_ACC * 8;
@@ -458,6 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       for (int v = 0; v < NS; ++v) {
         // ---- geometry + the 42 input channels -> A chunk 0 (lin_in operand) ----
         {
+          const long long tg0 = clock64();
           PointGeom pg = point_geometry(p.sc, sb, v, x, d);
           if (gsub == 0) {
             uint32_t* geo = reinterpret_cast<uint32_t*>(smem + SM_GEO) + grow * 8;
@@ -492,6 +510,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(bar_base + BAR_F_FULL * 8, 0);
           workers_sync();  // geometry visible to all worker warps
+          t_geo += clock64() - tg0;
         }
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
@@ -538,71 +557,111 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       }
       workers_sync();  // out_part is reused by the next tile
     }
+    if (threadIdx.x == 0) {
+      unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p.status + 2);
+      atomicAdd(cnt + 4, (unsigned long long)(clock64() - t_wstart));
+      atomicAdd(cnt + 5, (unsigned long long)t_acc);
+      atomicAdd(cnt + 6, (unsigned long long)t_geo);
+    }
   } else if (warp == WARP_MMA) {
-    if (lane == 0) {
-      if (rank == 0) {
-        // =============================== MMA issuer (leader CTA) ===============================
-        uint32_t seq = 0;          // weight-slot sequence number
-        uint32_t a_phase = 0, f_phase = 0;
-        const uint32_t a_base = smem_u32(smem + SM_A), b_base = smem_u32(smem + SM_B);
-        auto run_slot = [&](uint32_t dcol, uint32_t a_addr0, uint32_t a_addr1, int ksteps, bool overwrite_first) {
-          // one 16 KB weight slot: D[dcol] += A(a_addr0) * B  (+ A(a_addr1) * B if a_addr1 != 0)
-          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-          mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl);
-          mbar_wait(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl);
-          tc_fence_after();
-          const uint32_t b_addr = b_base + sl * SLOT_BYTES;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16_2sm(tmem_base + dcol, make_desc(a_addr0 + 32 * k), make_desc(b_addr + 32 * k), IDESC,
-                         (overwrite_first && k == 0) ? 0u : 1u);
-          if (a_addr1)
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_2sm(tmem_base + dcol, make_desc(a_addr1 + 32 * k), make_desc(b_addr + 32 * k), IDESC, 1u);
-          umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
-          ++seq;
-        };
-        auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
-          for (int jj = 0; jj < nchunks; ++jj) {
-            const int j = lin_in ? 0 : chunk_order(jj);
-            if (lin_in) {
-              mbar_wait(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220);
-            } else {
-              mbar_wait(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j);
-            }
-            tc_fence_after();
-            const uint32_t a_hi = a_base + j * A_CHUNK_BYTES, a_lo = a_hi + 8192;
-            for (int b = 0; b < 2; ++b) {
-              run_slot(dcol + b * 128, a_hi, a_lo, ksteps, overwrite && jj == 0);  // W_hi slot: Ahi*Whi + Alo*Whi
-              run_slot(dcol + b * 128, a_hi, 0, ksteps, false);                    // W_lo slot: Ahi*Wlo
-            }
+    if (rank == 0) {
+      // =============================== MMA issuer (leader CTA) ===============================
+      // The whole warp runs this loop with warp-uniform values (descriptors live in uniform registers); only the
+      // tcgen05.mma / tcgen05.commit instructions themselves are predicated on one elected lane.
+      uint32_t seq = 0;          // weight-slot sequence number
+      uint32_t a_phase = 0, f_phase = 0;
+      long long t_afull = 0, t_bfull = 0, t_bpeer = 0;
+      const long long t_start = clock64();
+      const uint32_t a_base = smem_u32(smem + SM_A), b_base = smem_u32(smem + SM_B);
+      const uint64_t desc0 = make_desc(0);   // address field is added per operand (16-byte units)
+      const bool issuer = elect_one();
+      auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
+        for (int jj = 0; jj < nchunks; ++jj) {
+          const int j = lin_in ? 0 : chunk_order(jj);
+          if (lin_in) {
+            mbar_wait_timed(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
+          } else {
+            mbar_wait_timed(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, t_afull);
           }
-          if (lin_in) f_phase ^= 1; else a_phase ^= 1;
-          umma_commit_pair(bar_base + BAR_ACC * 8);
-        };
-        for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-          for (int v = 0; v < NS; ++v) {
-            run_layer(X_COL, true, 1, 3, true);                 // lin_in (K = 42 -> 48)
-            for (int blk = 0; blk < 3; ++blk) {
-              run_layer(H_COL, true, 8, 4, false);              // fc_0
-              run_layer(X_COL, false, 8, 4, false);             // fc_1 accumulates onto the residual
+          const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
+          const uint64_t a_lo = a_hi + (8192 >> 4);
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint32_t d = tmem_base + dcol + b * 128;
+            // ---- W_hi slot: D += Ahi*Whi + Alo*Whi ----
+            {
+              const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+              mbar_wait_timed(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+              mbar_wait_timed(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+              tc_fence_after();
+              const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
+              if (issuer) {
+                umma_f16_2sm(d, a_hi, bd, IDESC, (overwrite && jj == 0) ? 0u : 1u);
+                umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
+                umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
+                if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
+                umma_f16_2sm(d, a_lo, bd, IDESC, 1u);
+                umma_f16_2sm(d, a_lo + 2, bd + 2, IDESC, 1u);
+                umma_f16_2sm(d, a_lo + 4, bd + 4, IDESC, 1u);
+                if (ksteps == 4) umma_f16_2sm(d, a_lo + 6, bd + 6, IDESC, 1u);
+                umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+              }
+              __syncwarp();
+              ++seq;
             }
-          }
-          for (int blk = 3; blk < 5; ++blk) {
-            run_layer(H_COL, true, 8, 4, false);
-            run_layer(X_COL, false, 8, 4, false);
+            // ---- W_lo slot: D += Ahi*Wlo ----
+            {
+              const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+              mbar_wait_timed(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+              mbar_wait_timed(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+              tc_fence_after();
+              const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
+              if (issuer) {
+                umma_f16_2sm(d, a_hi, bd, IDESC, 1u);
+                umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
+                umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
+                if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
+                umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+              }
+              __syncwarp();
+              ++seq;
+            }
           }
         }
-      } else {
-        // ============ peer CTA: forward "my half of the weight slot landed" to the leader ============
-        uint32_t seq = 0;
-        const uint32_t per_tile = (uint32_t)NS * (SLOTS_LIN_IN + 6 * SLOTS_FC) + 4 * SLOTS_FC;
-        for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-          for (uint32_t i = 0; i < per_tile; ++i) {
-            const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-            mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl);
-            mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
-            ++seq;
+        if (lin_in) f_phase ^= 1; else a_phase ^= 1;
+        if (issuer) umma_commit_pair(bar_base + BAR_ACC * 8);
+        __syncwarp();
+      };
+      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+        for (int v = 0; v < NS; ++v) {
+          run_layer(X_COL, true, 1, 3, true);                 // lin_in (K = 42 -> 48)
+          for (int blk = 0; blk < 3; ++blk) {
+            run_layer(H_COL, true, 8, 4, false);              // fc_0
+            run_layer(X_COL, false, 8, 4, false);             // fc_1 accumulates onto the residual
           }
+        }
+        for (int blk = 3; blk < 5; ++blk) {
+          run_layer(H_COL, true, 8, 4, false);
+          run_layer(X_COL, false, 8, 4, false);
+        }
+      }
+      if (lane == 0) {
+        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p.status + 2);
+        atomicAdd(cnt + 0, (unsigned long long)(clock64() - t_start));
+        atomicAdd(cnt + 1, (unsigned long long)t_afull);
+        atomicAdd(cnt + 2, (unsigned long long)t_bfull);
+        atomicAdd(cnt + 3, (unsigned long long)t_bpeer);
+      }
+    } else if (lane == 0) {
+      // ============ peer CTA: forward "my half of the weight slot landed" to the leader ============
+      uint32_t seq = 0;
+      const uint32_t per_tile = (uint32_t)NS * (SLOTS_LIN_IN + 6 * SLOTS_FC) + 4 * SLOTS_FC;
+      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
+        for (uint32_t i = 0; i < per_tile; ++i) {
+          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+          mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl);
+          mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
+          ++seq;
         }
       }
     }
@@ -610,10 +669,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     // =============================== weight streamer ===============================
     if (lane == 0) {
       uint32_t seq = 0;
+      long long t_empty = 0;
       const uint32_t b_base = smem_u32(smem + SM_B);
       auto stream_slot = [&](int slot_index) {
         const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-        mbar_wait(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl);
+        mbar_wait_timed(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl, t_empty);
         const uint32_t full = bar_base + (BAR_B_FULL + sl) * 8;
         mbar_expect_tx(full, SLOT_BYTES);
         bulk_g2s(b_base + sl * SLOT_BYTES, slots + (size_t)slot_index * SLOT_BYTES, SLOT_BYTES, full);
@@ -631,6 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         }
         for (int l = 6; l < 10; ++l) stream_fc(l);
       }
+      if (rank == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2) + 7, (unsigned long long)t_empty);
     }
   }
 
@@ -859,6 +920,20 @@ int pnr_tc_status(int* out) {
   PNR_CUDA(cudaMemcpy(&v, buf, sizeof(int), cudaMemcpyDeviceToHost));
   PNR_CUDA(cudaMemset(buf, 0, sizeof(int)));
   if (out) *out = v;
+  return PNR_OK;
+}
+
+
+// Debug: cycle breakdown accumulated over all launches since the last call (summed over clusters):
+// [0] MMA thread total, [1] MMA waits for A chunks, [2] for its own weight slot, [3] for the peer's slot,
+// [4] worker total, [5] worker waits for the accumulator, [6] geometry stage, [7] streamer waits for a free slot.
+int pnr_tc_counters(unsigned long long* out8) {
+  int* buf = nullptr;
+  int rc = tc::get_status_buffer(&buf);
+  if (rc) return rc;
+  PNR_CUDA(cudaDeviceSynchronize());
+  PNR_CUDA(cudaMemcpy(out8, buf + 2, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  PNR_CUDA(cudaMemset(buf + 2, 0, 8 * sizeof(unsigned long long)));
   return PNR_OK;
 }
 

@@ -141,6 +141,13 @@ def tc_status():
     return v.value
 
 
+def tc_counters():
+    arr = (C.c_ulonglong * 8)()
+    lib().pnr_tc_counters.restype = C.c_int
+    check(lib().pnr_tc_counters(arr))
+    return list(arr)
+
+
 def launch_count():
     return int(lib().pnr_launch_count())
 
