@@ -286,6 +286,43 @@ def cpu_reference_run(cfg, sample_rays, reps):
             "sample": f"{sample_rays} rays of the same C2 workload per pass (oracle/pnr_oracle.py, torch CPU fp32)"}
 
 
+def run_torch_eager(args):
+    """Context number, not the reference arm: the composed torch-op path of this repo (the same ATen op
+    sequence as the reference's PyTorch code: grid_sample, 15 addmm per chunk, cat/relu/...) on ONE GPU in fp32
+    (TF32 off, 50 000-point chunks) -- a stand-in for 'reference PyTorch eager on B200', which cannot be
+    imported on the GPU box."""
+    device = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = synth.CONFIGS[WORKLOAD]
+    net, renderer = build_scene(cfg, device, "simt")
+    rays = synth.make_rays(cfg, args.rays).to(device)[None]
+    class TorchField:            # a generic `model` callable for NeRFRenderer's composed path
+        use_viewdirs = True
+
+        def __call__(self, xyz, coarse=True, viewdirs=None):
+            return net._forward_autograd(xyz, coarse, viewdirs)
+
+    field = TorchField()
+
+    def step():
+        with torch.no_grad():
+            return renderer._forward_torch(field, rays, False)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"impl": "torch-eager", "metric": METRIC, "value": args.rays * args.steps / (ms / 1e3),
+                      "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms / args.steps,
+                      "dtype": "f32", "config": {"workload": "C2", "rays_per_step": args.rays,
+                                                  "note": "composed torch ops of this repo's autograd path under no_grad"}}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -317,7 +354,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--engine", default=os.environ.get("PNR_ENGINE", "auto"), choices=["auto", "simt", "tc"])
     ap.add_argument("--rays", type=int, default=16384, help="rays per step per GPU (16384 = one 128x128 frame)")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays per CPU-reference pass")
@@ -325,5 +362,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch-eager":
+        run_torch_eager(a)
     else:
         run_ours(a)

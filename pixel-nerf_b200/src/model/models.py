@@ -254,6 +254,10 @@ class PixelNeRFNet(torch.nn.Module):
                                       B, eng, ws.data_ptr(), ws.numel(), pn.stream_ptr(dev)))
         return out
 
+    def _torch_field(self, xyz, coarse=True, viewdirs=None, far=False):
+        """The composed-torch field as a plain callable (bench.py --impl torch-eager; use_viewdirs protocol)."""
+        return self._forward_autograd(xyz, coarse, viewdirs)
+
     def _forward_autograd(self, xyz, coarse, viewdirs):
         """Differentiable composed-torch evaluation (training only)."""
         SB, B, _ = xyz.shape
