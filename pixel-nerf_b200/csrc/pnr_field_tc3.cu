@@ -16,6 +16,7 @@
 //     consumed position pos - NA (tcgen05.commit multicast to both CTAs' F barriers);
 //   * lin_out (512 -> 4) is one more tensor-core layer with N = 16, so no cross-CTA reduction is needed.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "pnr_common.cuh"
 #include "pnr_geom.cuh"
@@ -41,8 +42,9 @@ constexpr uint32_t X_COL = 0, H_COL = 256;
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + NA * A_SLOT;
 constexpr int SM_BAR = SM_B + NB * B_SLOT;          // 229376
-constexpr int BAR_W = 0;                             // [NA] chunk written (16 warp arrivals)
-constexpr int BAR_F = BAR_W + NA;                    // [NA] slot free in BOTH CTAs (2 commits)
+constexpr int BAR_WL = 0;                            // [NA] chunk written by my own workers (16 warp arrivals)
+constexpr int BAR_WR = BAR_WL + NA;                  // [NA] chunk written by the peer (st.async complete_tx, 32 KB)
+constexpr int BAR_F = BAR_WR + NA;                   // [NA] slot free in BOTH CTAs (2 commits)
 constexpr int BAR_BF = BAR_F + NA;                   // [NB] weight slot landed (tx)
 constexpr int BAR_BE = BAR_BF + NB;                  // [NB] weight slot free (commit)
 constexpr int BAR_ACC = BAR_BE + NB;
@@ -70,12 +72,12 @@ struct Params {
   int64_t total_points;
   int64_t n_tiles;
   int* status;
+  int debug;   // experiment switches (PNR_TC3_DEBUG): 2 = no gather loads, 4 = no MMA issue
 };
 
 enum { MODE_GATHER = 0, MODE_BIAS_WB = 1, MODE_HIDDEN = 2, MODE_COMBINE = 3, MODE_FINAL = 4 };
 
 struct WorkerCtx {
-  uint8_t* smem;
   uint32_t smem_u;      // shared::cta address of smem base
   uint32_t peer_u;      // the same offset in the peer CTA (shared::cluster address)
   uint32_t tmem;        // base tmem address incl. this warp's lane quarter
@@ -83,8 +85,6 @@ struct WorkerCtx {
   uint32_t rank;
   int lane, s, row;
   float w_scale, w_inv;
-  long long* t_acc;
-  long long* t_free;
 };
 
 __device__ __forceinline__ void gather_issue(float4* g, const float* __restrict__ proj_i, const uint32_t* off, int n0) {
@@ -96,43 +96,90 @@ __device__ __forceinline__ void gather_issue(float4* g, const float* __restrict_
   }
 }
 
+// TMEM load of 8 columns WITHOUT waiting: the registers are valid only after tmem_ld_wait8 (which carries them as
+// in/out operands so that no use can be scheduled ahead of the wait).
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// relu(y0), relu(y1) -> packed fp16 hi pair and lo pair (error-compensated split); F2FP packs two values per
+// instruction on the fast pipe and saturates instead of producing inf.
+__device__ __forceinline__ void split_relu2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  const float a0 = fmaxf(y0, 0.f), a1 = fmaxf(y1, 0.f);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(a1 - hf.y), "f"(a0 - hf.x));
+}
+
 // One epilogue pass over this thread's 64 local features (4 waves x 2 steps of 8) of one layer.
 //   pos_base: ring position of the first chunk of the layer that will consume what this pass produces.
+// TMEM loads, gathers and bias loads of step i+1 are issued before step i is processed.
 template <int MODE>
 __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
                                          const uint32_t* off, const float* wt, int view, float* __restrict__ scratch,
-                                         uint32_t pos_base, uint32_t acc_phase, int tag) {
-  float4 g[2][8];
+                                         uint32_t pos_base, uint32_t acc_phase, int tag, long long& t_acc) {
+  float4 g[8];      // gather taps of the CURRENT step; refilled for the next step right after use
+  float4 bb[2][2];
+  uint32_t raw[8];
   const int n_base = (int)c.rank * HALF;   // global index of this CTA's first feature
-  if (MODE == MODE_GATHER) gather_issue(g[0], proj_i, off, n_base + c.s * 16);  // in flight during the MMA tail
-  mbar_wait_timed(c.bar_base + BAR_ACC * 8, acc_phase, p.status, tag, *c.t_acc);
+  const bool do_gather = !(p.debug & 2);
+  if (MODE == MODE_GATHER) {
+    if (do_gather) {
+      gather_issue(g, proj_i, off, n_base + c.s * 16);  // in flight during the MMA tail
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    bb[0][0] = __ldg(reinterpret_cast<const float4*>(bias + n_base + c.s * 16));
+    bb[0][1] = __ldg(reinterpret_cast<const float4*>(bias + n_base + c.s * 16) + 1);
+  }
+  mbar_wait_timed(c.bar_base + BAR_ACC * 8, acc_phase, p.status, tag, t_acc);
   tc_fence_after();
+  tmem_ld8_issue(c.tmem + acc_col + c.s * 16, raw);
   const int NS = p.sc.NS;
   const bool produce = !(MODE == MODE_COMBINE && view != NS - 1);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int wave = i >> 1, h = i & 1;
     const int f = wave * 64 + c.s * 16 + h * 8;   // local feature = TMEM column inside the accumulator
-    const int n0 = n_base + f;
+    const int fn = ((i + 1) >> 1) * 64 + c.s * 16 + ((i + 1) & 1) * 8;   // next step's
     float y[8];
+    tmem_ld_wait8(raw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(raw[e]) * c.w_inv;
+    if (i + 1 < 8) {
+      tmem_ld8_issue(c.tmem + acc_col + fn, raw);
+      if (MODE != MODE_GATHER) {
+        bb[(i + 1) & 1][0] = __ldg(reinterpret_cast<const float4*>(bias + n_base + fn));
+        bb[(i + 1) & 1][1] = __ldg(reinterpret_cast<const float4*>(bias + n_base + fn) + 1);
+      }
+    }
     if (MODE == MODE_GATHER) {
-      if (i + 1 < 8) gather_issue(g[(i + 1) & 1], proj_i, off, n_base + ((i + 1) >> 1) * 64 + c.s * 16 + ((i + 1) & 1) * 8);
-      tmem_ld8(c.tmem + acc_col + f, y);
-      const float4* t = g[i & 1];
+      const float4* t = g;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        y[4 * hh + 0] = y[4 * hh + 0] * c.w_inv + (((t[0 + hh].x * wt[0] + t[2 + hh].x * wt[1]) + t[4 + hh].x * wt[2]) + t[6 + hh].x * wt[3]);
-        y[4 * hh + 1] = y[4 * hh + 1] * c.w_inv + (((t[0 + hh].y * wt[0] + t[2 + hh].y * wt[1]) + t[4 + hh].y * wt[2]) + t[6 + hh].y * wt[3]);
-        y[4 * hh + 2] = y[4 * hh + 2] * c.w_inv + (((t[0 + hh].z * wt[0] + t[2 + hh].z * wt[1]) + t[4 + hh].z * wt[2]) + t[6 + hh].z * wt[3]);
-        y[4 * hh + 3] = y[4 * hh + 3] * c.w_inv + (((t[0 + hh].w * wt[0] + t[2 + hh].w * wt[1]) + t[4 + hh].w * wt[2]) + t[6 + hh].w * wt[3]);
+        y[4 * hh + 0] += ((t[0 + hh].x * wt[0] + t[2 + hh].x * wt[1]) + t[4 + hh].x * wt[2]) + t[6 + hh].x * wt[3];
+        y[4 * hh + 1] += ((t[0 + hh].y * wt[0] + t[2 + hh].y * wt[1]) + t[4 + hh].y * wt[2]) + t[6 + hh].y * wt[3];
+        y[4 * hh + 2] += ((t[0 + hh].z * wt[0] + t[2 + hh].z * wt[1]) + t[4 + hh].z * wt[2]) + t[6 + hh].z * wt[3];
+        y[4 * hh + 3] += ((t[0 + hh].w * wt[0] + t[2 + hh].w * wt[1]) + t[4 + hh].w * wt[2]) + t[6 + hh].w * wt[3];
       }
+      if (i + 1 < 8 && do_gather) gather_issue(g, proj_i, off, n_base + fn);  // taps of the next step, in flight during the stores below
     } else {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
-      tmem_ld8(c.tmem + acc_col + f, y);
-      y[0] = y[0] * c.w_inv + b0.x; y[1] = y[1] * c.w_inv + b0.y; y[2] = y[2] * c.w_inv + b0.z; y[3] = y[3] * c.w_inv + b0.w;
-      y[4] = y[4] * c.w_inv + b1.x; y[5] = y[5] * c.w_inv + b1.y; y[6] = y[6] * c.w_inv + b1.z; y[7] = y[7] * c.w_inv + b1.w;
+      const float4 b0 = bb[i & 1][0], b1 = bb[i & 1][1];
+      y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+      y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
     }
     if (MODE == MODE_COMBINE && NS > 1) {
       // multi-view mean (util.combine_interleaved): sum in view order, then divide
@@ -165,30 +212,30 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
       const uint32_t slot_l = pos_l % NA, slot_r = pos_r % NA;
       if (h == 0) {
         // both CTAs must have consumed the previous occupants of the two slots
-        mbar_wait_timed(c.bar_base + (BAR_F + slot_l) * 8, ((pos_l / NA) + 1) & 1, p.status, 500 + slot_l, *c.t_free);
-        mbar_wait_timed(c.bar_base + (BAR_F + slot_r) * 8, ((pos_r / NA) + 1) & 1, p.status, 510 + slot_r, *c.t_free);
+        mbar_wait(c.bar_base + (BAR_F + slot_l) * 8, ((pos_l / NA) + 1) & 1, p.status, 500 + slot_l);
+        mbar_wait(c.bar_base + (BAR_F + slot_r) * 8, ((pos_r / NA) + 1) & 1, p.status, 510 + slot_r);
       }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) hi[e] = split_pack(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f), lo[e]);
+      uint4 vhi, vlo;
+      split_relu2(y[0], y[1], vhi.x, vlo.x);
+      split_relu2(y[2], y[3], vhi.y, vlo.y);
+      split_relu2(y[4], y[5], vhi.z, vlo.z);
+      split_relu2(y[6], y[7], vhi.w, vlo.w);
       const uint32_t in_slot = (uint32_t)c.row * 128 + (uint32_t)(((2 * c.s + h) ^ (c.row & 7)) * 16);
-      const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      uint8_t* lp = c.smem + SM_A + slot_l * A_SLOT + in_slot;
-      *reinterpret_cast<uint4*>(lp) = vhi;
-      *reinterpret_cast<uint4*>(lp + 16384) = vlo;
+      const uint32_t lp = c.smem_u + SM_A + slot_l * A_SLOT + in_slot;
+      st_shared_v4(lp, vhi);
+      st_shared_v4(lp + 16384, vlo);
+      // peer's copy: asynchronous DSMEM stores that complete_tx on the peer's WR barrier (no fence, no arrive)
       const uint32_t rp = c.peer_u + SM_A + slot_r * A_SLOT + in_slot;
-      st_cluster_v4(rp, vhi);
-      st_cluster_v4(rp + 16384, vlo);
+      const uint32_t rbar = c.peer_u + SM_BAR + (BAR_WR + slot_r) * 8;
+      st_async_v4(rp, vhi, rbar);
+      st_async_v4(rp + 16384, vlo, rbar);
       if (h == 1) {
-        // this warp's 32 x 16 slice of chunk `wave` is in place in both CTAs: publish
-        fence_proxy_async_all();
+        // this warp's 32 x 16 slice of my own copy of chunk `wave` is in place: publish to my MMA warp
+        fence_proxy_async();
         if (MODE != MODE_HIDDEN && MODE != MODE_FINAL) tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (c.lane == 0) {
-          mbar_arrive(c.bar_base + (BAR_W + slot_l) * 8);
-          mbar_arrive_cta_release(c.bar_base + (BAR_W + slot_r) * 8, c.rank ^ 1);
-        }
+        if (c.lane == 0) mbar_arrive(c.bar_base + (BAR_WL + slot_l) * 8);
       }
     }
   }
@@ -207,7 +254,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar_base + (BAR_W + i) * 8, NWORKER_WARPS);
+      mbar_init(bar_base + (BAR_WL + i) * 8, NWORKER_WARPS);
+      mbar_init(bar_base + (BAR_WR + i) * 8, 1);
       mbar_init(bar_base + (BAR_F + i) * 8, 2);
     }
     for (int i = 0; i < NB; ++i) {
@@ -239,7 +287,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
   if (warp < NWORKER_WARPS) {
     // =============================== worker warps ===============================
     WorkerCtx c;
-    c.smem = smem;
     c.smem_u = smem_u;
     c.peer_u = mapa_cluster(smem_u, rank ^ 1);
     c.lane = lane;
@@ -252,8 +299,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.w_scale = w_scale;
     c.w_inv = w_inv;
     long long t_acc = 0, t_free = 0;
-    c.t_acc = &t_acc;
-    c.t_free = &t_free;
     const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * HALF * ROWS;
     uint32_t acc_phase = 0;
@@ -297,38 +342,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
             *reinterpret_cast<uint32_t*>(row_hi + byte) = hi;
             *reinterpret_cast<uint32_t*>(row_lo + byte) = lo;
           }
-          fence_proxy_async_all();
+          fence_proxy_async();
           tc_fence_before();   // this warp's earlier TMEM reads precede the next lin_in MMA
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_base + (BAR_W + slot) * 8);
+          if (lane == 0) mbar_arrive(bar_base + (BAR_WL + slot) * 8);
           pos += 1;
         }
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
           epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, off, wt, v, nullptr, pos,
-                                acc_phase, 100 + blk);   // X ready -> A of fc_0
+                                acc_phase, 100 + blk, t_acc);   // X ready -> A of fc_0
           acc_phase ^= 1;
           pos += 8;
           epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, off, wt, v, nullptr, pos, acc_phase,
-                                110 + blk);              // H ready -> A of fc_1
+                                110 + blk, t_acc);              // H ready -> A of fc_1
           acc_phase ^= 1;
           pos += 8;
         }
-        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, off, wt, v, scratch, pos, acc_phase, 120);
+        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, off, wt, v, scratch, pos, acc_phase, 120, t_acc);
         acc_phase ^= 1;
       }
       pos += 8;  // fc_0 of block 3 consumed what the last view's COMBINE produced
       // ---- blocks 3..4 on the view-averaged rows ----
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 130);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 130, t_acc);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 131);
+      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 131, t_acc);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 132);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 132, t_acc);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_FINAL>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 133);
+      epilogue<MODE_FINAL>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 133, t_acc);
       acc_phase ^= 1;
       pos += 8;
       // ---- lin_out accumulator (16 columns at H_COL): sigmoid rgb / relu sigma (models.py:260-264) ----
@@ -364,12 +409,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     const uint32_t a_base = smem_u + SM_A, b_base = smem_u + SM_B;
     const uint64_t desc0 = make_desc(0);
     const bool issuer = elect_one();
+    const bool do_mma = !(p.debug & 4);
+    // wait until ring slot `slot` holds the next chunk: my workers arrive on WL; the peer's st.async stores
+    // complete_tx 32 KB on WR (armed here).  The DSMEM data arrives through the generic proxy, so a proxy fence
+    // precedes the tensor core's (async proxy) reads.
+    uint32_t wl_par = 0, wr_par = 0;   // phase parity per slot
+    auto wait_chunk = [&](uint32_t slot, bool remote_written) {
+      if (remote_written) {
+        if (issuer) mbar_expect_tx(bar_base + (BAR_WR + slot) * 8, A_SLOT);
+        mbar_wait_timed(bar_base + (BAR_WR + slot) * 8, (wr_par >> slot) & 1, p.status, 230 + slot, t_w);
+        wr_par ^= 1u << slot;
+        fence_proxy_async();
+      } else {
+        mbar_wait_timed(bar_base + (BAR_WL + slot) * 8, (wl_par >> slot) & 1, p.status, 220 + slot, t_w);
+        wl_par ^= 1u << slot;
+      }
+      tc_fence_after();
+    };
     // one ring position: D[dcol] (+)= A(pos) * W^T for this CTA's 256 output features
     auto fc_position = [&](uint32_t dcol, bool overwrite, int ksteps, bool remote_written) {
-      const uint32_t slot = pos % NA, par = (pos / NA) & 1;
-      if (remote_written) mbar_wait_cluster(bar_base + (BAR_W + slot) * 8, par, p.status, 230 + slot, t_w);
-      else mbar_wait_timed(bar_base + (BAR_W + slot) * 8, par, p.status, 220 + slot, t_w);
-      tc_fence_after();
+      const uint32_t slot = pos % NA;
+      wait_chunk(slot, remote_written);
       const uint64_t a_hi = desc0 + ((a_base + slot * A_SLOT) >> 4);
       const uint64_t a_lo = a_hi + (16384 >> 4);
       const uint32_t d = tmem_base + dcol;
@@ -379,14 +439,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         tc_fence_after();
         const uint64_t bd = desc0 + ((b_base + sl * B_SLOT) >> 4);
         if (issuer) {
-          umma_f16_1sm(d, a_hi, bd, IDESC_M128_N256, overwrite ? 0u : 1u);
-          umma_f16_1sm(d, a_hi + 2, bd + 2, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_hi + 4, bd + 4, IDESC_M128_N256, 1u);
-          if (ksteps == 4) umma_f16_1sm(d, a_hi + 6, bd + 6, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_lo, bd, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_lo + 2, bd + 2, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_lo + 4, bd + 4, IDESC_M128_N256, 1u);
-          if (ksteps == 4) umma_f16_1sm(d, a_lo + 6, bd + 6, IDESC_M128_N256, 1u);
+          if (do_mma) {
+            umma_f16_1sm(d, a_hi, bd, IDESC_M128_N256, overwrite ? 0u : 1u);
+            umma_f16_1sm(d, a_hi + 2, bd + 2, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_hi + 4, bd + 4, IDESC_M128_N256, 1u);
+            if (ksteps == 4) umma_f16_1sm(d, a_hi + 6, bd + 6, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_lo, bd, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_lo + 2, bd + 2, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_lo + 4, bd + 4, IDESC_M128_N256, 1u);
+            if (ksteps == 4) umma_f16_1sm(d, a_lo + 6, bd + 6, IDESC_M128_N256, 1u);
+          }
           umma_commit_local(bar_base + (BAR_BE + sl) * 8);
         }
         __syncwarp();
@@ -398,10 +460,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         tc_fence_after();
         const uint64_t bd = desc0 + ((b_base + sl * B_SLOT) >> 4);
         if (issuer) {
-          umma_f16_1sm(d, a_hi, bd, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_hi + 2, bd + 2, IDESC_M128_N256, 1u);
-          umma_f16_1sm(d, a_hi + 4, bd + 4, IDESC_M128_N256, 1u);
-          if (ksteps == 4) umma_f16_1sm(d, a_hi + 6, bd + 6, IDESC_M128_N256, 1u);
+          if (do_mma) {
+            umma_f16_1sm(d, a_hi, bd, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_hi + 2, bd + 2, IDESC_M128_N256, 1u);
+            umma_f16_1sm(d, a_hi + 4, bd + 4, IDESC_M128_N256, 1u);
+            if (ksteps == 4) umma_f16_1sm(d, a_hi + 6, bd + 6, IDESC_M128_N256, 1u);
+          }
           umma_commit_local(bar_base + (BAR_BE + sl) * 8);
           umma_commit_both(bar_base + (BAR_F + slot) * 8);   // ring slot consumed (seen by both CTAs)
         }
@@ -435,10 +499,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         mbar_wait_timed(bar_base + (BAR_BF + sl) * 8, ph, p.status, 240 + sl, t_b);
         const uint32_t d = tmem_base + H_COL;
         for (int t = 0; t < 8; ++t) {
-          const uint32_t slot = pos % NA, par = (pos / NA) & 1;
-          if (t & 1) mbar_wait_cluster(bar_base + (BAR_W + slot) * 8, par, p.status, 250 + slot, t_w);
-          else mbar_wait_timed(bar_base + (BAR_W + slot) * 8, par, p.status, 260 + slot, t_w);
-          tc_fence_after();
+          const uint32_t slot = pos % NA;
+          wait_chunk(slot, (t & 1) != 0);
           const uint64_t a_hi = desc0 + ((a_base + slot * A_SLOT) >> 4);
           const uint64_t a_lo = a_hi + (16384 >> 4);
           const uint64_t b_hi = desc0 + ((b_base + sl * B_SLOT + kidx_of(t, rank) * 2048) >> 4);
@@ -585,6 +647,10 @@ int tc3_field_eval(const PnrScene& sc, const PnrMlp& mlp, const uint8_t* packed3
   p.total_points = total_points;
   p.n_tiles = (total_points + tc3::ROWS - 1) / tc3::ROWS;
   p.status = status;
+  {
+    const char* e = getenv("PNR_TC3_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -201,6 +201,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// asynchronous DSMEM store: 16 bytes to the peer's shared memory, completing 16 tx-bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
 __device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
