@@ -39,12 +39,13 @@ int tc3_field_eval(const PnrScene& sc, const PnrMlp& mlp, const uint8_t* packed3
                    const PointSource& src, int64_t total_points, float* out, void* ws, int pairs, int* status,
                    cudaStream_t s);
 
-// Which tensor-engine mapping runs: 3 = N-split pair (pnr_field_tc3.cu, default), 2 = M-split pair (this file).
+// Which tensor-engine mapping runs: 2 = M-split pair (this file; default, fastest measured), 3 = N-split pair
+// (pnr_field_tc3.cu).  PNR_TC_VARIANT selects.
 static int tc_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PNR_TC_VARIANT");
-    v = (e && e[0] == '2') ? 2 : 3;
+    v = (e && e[0] == '3') ? 3 : 2;
   }
   return v;
 }
@@ -58,7 +59,7 @@ constexpr int NWORKER_WARPS = 16;
 constexpr int WARP_MMA = NWORKER_WARPS;       // warp 16: MMA issue (leader) / slot forwarder (peer)
 constexpr int NTHREADS = (NWORKER_WARPS + 2) * 32;  // + warp 17: weight streamer
 constexpr int SLOT_BYTES = 16384;        // 128 weight rows x 64 k x fp16
-constexpr int NSLOTS = 5;
+constexpr int NSLOTS = 6;
 constexpr int A_CHUNK_BYTES = 16384;     // 64 rows x 64 k x fp16, hi then lo
 constexpr int A_BYTES = 8 * A_CHUNK_BYTES;
 constexpr int SLOTS_LIN_IN = 4;
@@ -70,18 +71,19 @@ constexpr uint32_t X_COL = 0, H_COL = 256;
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + A_BYTES;                    // 131072
-constexpr int SM_GEO = SM_B + NSLOTS * SLOT_BYTES;      // 212992: [64][8] words
-constexpr int SM_PART = SM_GEO + ROWS * 8 * 4;          // 215040: [64][4][4] floats
-constexpr int SM_BAR = SM_PART + ROWS * 32 * 4;         // out partials: [64][8][4] floats
+constexpr int SM_GEO = SM_B + NSLOTS * SLOT_BYTES;      // [64][8] words: 4 tap offsets + 4 bilinear weights per row
+constexpr int SM_PART = SM_A;                           // lin_out partials [64][8][4] floats alias A chunk 0 (free at tile end)
+constexpr int SM_BAR = SM_GEO + ROWS * 8 * 4;
 constexpr int SM_TOTAL = SM_BAR + 512;
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;             // + alignment slack
+constexpr int SMEM_BYTES = SM_TOTAL;
 
 // barrier indices (8 bytes each)
 constexpr int BAR_B_FULL = 0;                 // [NSLOTS]
 constexpr int BAR_B_PEER = BAR_B_FULL + NSLOTS;   // [NSLOTS] (leader only)
 constexpr int BAR_B_EMPTY = BAR_B_PEER + NSLOTS;  // [NSLOTS]
 constexpr int BAR_A_FULL = BAR_B_EMPTY + NSLOTS;  // [8]
-constexpr int BAR_F_FULL = BAR_A_FULL + 8;
+constexpr int BAR_A_FREE = BAR_A_FULL + 8;         // [8] chunk consumed by the MMA of the current fc layer
+constexpr int BAR_F_FULL = BAR_A_FREE + 8;
 constexpr int BAR_ACC = BAR_F_FULL + 1;
 constexpr int BAR_COUNT = BAR_ACC + 1;
 constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
@@ -107,6 +109,7 @@ enum { MODE_GATHER = 0, MODE_BIAS_WB = 1, MODE_HIDDEN = 2, MODE_COMBINE = 3, MOD
 
 struct WorkerCtx {
   uint8_t* smem;
+  uint32_t smem_u;      // shared::cta address of the smem base
   uint32_t tmem;        // base tmem address incl. this warp's lane quarter
   uint32_t bar_base;    // smem address of the barrier array
   int lane, s, m, n_hi;
@@ -125,37 +128,126 @@ __device__ __forceinline__ uint32_t step_tmem_col(const WorkerCtx& c, int i) {
   return (uint32_t)((i >> 2) * 128 + ((i >> 1) & 1) * 64 + c.s * 16 + (i & 1) * 8);
 }
 
-__device__ __forceinline__ void gather_issue(float4* g, const float* __restrict__ proj_i, const uint32_t* off, int n0) {
+// TMEM load of 8 columns WITHOUT waiting: the registers are valid only after tmem_ld_wait8 (which carries them as
+// in/out operands so that no use can be scheduled ahead of the wait).
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// relu(y0), relu(y1) -> packed fp16 hi pair and lo pair (error-compensated split); F2FP packs two values per
+// instruction on the fast pipe and saturates instead of producing inf.
+__device__ __forceinline__ void split_relu2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  const float a0 = fmaxf(y0, 0.f), a1 = fmaxf(y1, 0.f);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(a1 - hf.y), "f"(a0 - hf.x));
+}
+
+// Where the 16-byte hi unit of (row m, features [8u, 8u+8) of k-chunk j) lives in the A buffer; the lo unit is
+// 8192 bytes further.  The SAME two slots first hold the staged gather values G[m][8u..8u+3] and G[m][8u+4..8u+7].
+__device__ __forceinline__ uint32_t a_unit_offset(int j, int m, int u) {
+  return (uint32_t)(SM_A + j * A_CHUNK_BYTES + m * 128 + ((u ^ (m & 7)) * 16));
+}
+
+// Coalesced gather of the projected-latent map for one ResNet block: G[row][:] = sum_k w_k * P_i[tap_k(row)][:].
+// A warp takes one row at a time and its 32 lanes read 512 contiguous bytes per tap (4 wavefronts per load instead of
+// the 32 a lane-per-row gather costs); the result is parked in the (currently free) A-operand buffer, in exactly the
+// two 16-byte slots that the thread owning (row, 8 features) overwrites with its fp16 hi/lo units later.
+__device__ __forceinline__ void stage_gather(uint8_t* smem, uint32_t smem_u, const float* __restrict__ proj_i, int warp,
+                                             int lane) {
+  const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
+  float4 t[4], tn[4];
+  // 64 rows / 16 warps = 4 rows per warp, 4 spans of 128 features per row
+  auto issue = [&](float4* dst, int it) {
+    const int row = warp * 4 + (it >> 2), sp = it & 3;
+    const uint32_t* geo = geo_all + row * 8;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4* src = reinterpret_cast<const float4*>(proj_i + off[k] + n0);
-    g[2 * k] = __ldg(src);
-    g[2 * k + 1] = __ldg(src + 1);
+    for (int k = 0; k < 4; ++k) dst[k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + sp * 128) + lane);
+  };
+  issue(t, 0);
+#pragma unroll 1
+  for (int it = 0; it < 16; ++it) {
+    if (it + 1 < 16) issue(tn, it + 1);
+    const int row = warp * 4 + (it >> 2), sp = it & 3;
+    const uint32_t* geo = geo_all + row * 8;
+    const float w0 = __uint_as_float(geo[4]), w1 = __uint_as_float(geo[5]), w2 = __uint_as_float(geo[6]),
+                w3 = __uint_as_float(geo[7]);
+    float4 g;
+    g.x = ((t[0].x * w0 + t[1].x * w1) + t[2].x * w2) + t[3].x * w3;
+    g.y = ((t[0].y * w0 + t[1].y * w1) + t[2].y * w2) + t[3].y * w3;
+    g.z = ((t[0].z * w0 + t[1].z * w1) + t[2].z * w2) + t[3].z * w3;
+    g.w = ((t[0].w * w0 + t[1].w * w1) + t[2].w * w2) + t[3].w * w3;
+    // lane -> features [sp*128 + 4*lane, +4): chunk j = 2*sp + lane/16, unit u = (lane%16)/2, hi slot if lane even
+    const int j = 2 * sp + (lane >> 4), u = (lane & 15) >> 1;
+    st_shared_f4(smem_u + a_unit_offset(j, row, u) + ((lane & 1) ? 8192u : 0u), g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = tn[k];
   }
 }
 
-// One epilogue pass over this thread's 64 features of one layer.
-//   acc_col : TMEM column base of the accumulator read (X_COL or H_COL)
-//   bias    : per-feature vector added (all modes but GATHER);  proj_i: projected-latent map (GATHER)
+// The same for ONE k-chunk (64 features) of all 64 rows: 16 lanes cover a row's 64 features, a warp-load fetches two
+// rows.  Used to stage the next block's gather chunk by chunk while the tensor core is still consuming the rest of
+// the A buffer.
+__device__ __forceinline__ void stage_gather_chunk(uint8_t* smem, uint32_t smem_u, const float* __restrict__ proj_i,
+                                                   int j, int warp, int lane) {
+  const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
+  const int sub = lane >> 4, l16 = lane & 15;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int row = warp * 4 + it * 2 + sub;
+    const uint32_t* geo = geo_all + row * 8;
+    float4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + j * 64) + l16);
+    const float w0 = __uint_as_float(geo[4]), w1 = __uint_as_float(geo[5]), w2 = __uint_as_float(geo[6]),
+                w3 = __uint_as_float(geo[7]);
+    float4 g;
+    g.x = ((t[0].x * w0 + t[1].x * w1) + t[2].x * w2) + t[3].x * w3;
+    g.y = ((t[0].y * w0 + t[1].y * w1) + t[2].y * w2) + t[3].y * w3;
+    g.z = ((t[0].z * w0 + t[1].z * w1) + t[2].z * w2) + t[3].z * w3;
+    g.w = ((t[0].w * w0 + t[1].w * w1) + t[2].w * w2) + t[3].w * w3;
+    st_shared_f4(smem_u + a_unit_offset(j, row, l16 >> 1) + ((l16 & 1) ? 8192u : 0u), g);
+  }
+}
+
+// One epilogue pass over this thread's 64 features of one layer (8 steps of 8).  TMEM loads and bias loads of step
+// i+1 are issued before step i is processed; MODE_GATHER reads the staged gather values back from shared memory.
 template <int MODE>
 __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
                                          int view, float* __restrict__ scratch, float* out_part, uint32_t acc_bar,
                                          uint32_t acc_phase, int tag) {
-  uint32_t off[4];
-  float wt[4];
-  float4 g[2][8];
-  if (MODE == MODE_GATHER) {
-    const uint32_t* geo = reinterpret_cast<const uint32_t*>(c.smem + SM_GEO) + c.m * 8;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      off[k] = geo[k];
-      wt[k] = __uint_as_float(geo[4 + k]);
-    }
-    gather_issue(g[0], proj_i, off, step_feature(c, 0));  // in flight while the MMA of this layer finishes
+  float4 bb[2][2];
+  uint32_t raw[8];
+  if (MODE != MODE_GATHER) {
+    bb[0][0] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, 0)));
+    bb[0][1] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, 0)) + 1);
   }
-  mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
-  tc_fence_after();
+  if (MODE == MODE_GATHER) {
+    // the accumulator barrier was already passed by the caller (the gather had to be staged after it)
+  } else {
+    mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
+    tc_fence_after();
+  }
+  tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, 0), raw);
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   const int NS = p.sc.NS;
   const bool produce = (MODE != MODE_OUT) && !(MODE == MODE_COMBINE && view != NS - 1);
@@ -163,24 +255,27 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
   for (int i = 0; i < 8; ++i) {
     const int n0 = step_feature(c, i);
     const uint32_t col = step_tmem_col(c, i);
+    const int j = 4 * (i >> 2) + 2 * c.n_hi + ((i >> 1) & 1);
+    const uint32_t unit = c.smem_u + a_unit_offset(j, c.m, 2 * c.s + (i & 1));
     float y[8];
-    if (MODE == MODE_GATHER) {
-      if (i + 1 < 8) gather_issue(g[(i + 1) & 1], proj_i, off, step_feature(c, i + 1));
-      tmem_ld8(c.tmem + acc_col + col, y);
-      const float4* t = g[i & 1];
+    tmem_ld_wait8(raw);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        y[4 * hh + 0] = y[4 * hh + 0] * c.w_inv + (((t[0 + hh].x * wt[0] + t[2 + hh].x * wt[1]) + t[4 + hh].x * wt[2]) + t[6 + hh].x * wt[3]);
-        y[4 * hh + 1] = y[4 * hh + 1] * c.w_inv + (((t[0 + hh].y * wt[0] + t[2 + hh].y * wt[1]) + t[4 + hh].y * wt[2]) + t[6 + hh].y * wt[3]);
-        y[4 * hh + 2] = y[4 * hh + 2] * c.w_inv + (((t[0 + hh].z * wt[0] + t[2 + hh].z * wt[1]) + t[4 + hh].z * wt[2]) + t[6 + hh].z * wt[3]);
-        y[4 * hh + 3] = y[4 * hh + 3] * c.w_inv + (((t[0 + hh].w * wt[0] + t[2 + hh].w * wt[1]) + t[4 + hh].w * wt[2]) + t[6 + hh].w * wt[3]);
+    for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(raw[e]) * c.w_inv;
+    if (i + 1 < 8) {
+      tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, i + 1), raw);
+      if (MODE != MODE_GATHER) {
+        bb[(i + 1) & 1][0] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, i + 1)));
+        bb[(i + 1) & 1][1] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, i + 1)) + 1);
       }
+    }
+    if (MODE == MODE_GATHER) {
+      const float4 g0 = ld_shared_f4(unit), g1 = ld_shared_f4(unit + 8192);
+      y[0] += g0.x; y[1] += g0.y; y[2] += g0.z; y[3] += g0.w;
+      y[4] += g1.x; y[5] += g1.y; y[6] += g1.z; y[7] += g1.w;
     } else {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
-      tmem_ld8(c.tmem + acc_col + col, y);
-      y[0] = y[0] * c.w_inv + b0.x; y[1] = y[1] * c.w_inv + b0.y; y[2] = y[2] * c.w_inv + b0.z; y[3] = y[3] * c.w_inv + b0.w;
-      y[4] = y[4] * c.w_inv + b1.x; y[5] = y[5] * c.w_inv + b1.y; y[6] = y[6] * c.w_inv + b1.z; y[7] = y[7] * c.w_inv + b1.w;
+      const float4 b0 = bb[i & 1][0], b1 = bb[i & 1][1];
+      y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+      y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
     }
     if (MODE == MODE_COMBINE && NS > 1) {
       // multi-view mean (util.combine_interleaved): sum in view order, then divide
@@ -224,15 +319,14 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
         o3 = fmaf(a3, w3.w, fmaf(a2, w3.z, fmaf(a1, w3.y, fmaf(a0, w3.x, o3))));
       }
     } else if (produce) {
-      // relu -> fp16 hi/lo -> one 16-byte unit of the swizzled A tile (row m, unit 2s+h of chunk j)
-      const int j = 4 * (i >> 2) + 2 * c.n_hi + ((i >> 1) & 1);
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) hi[e] = split_pack(fmaxf(y[2 * e], 0.f), fmaxf(y[2 * e + 1], 0.f), lo[e]);
-      uint8_t* row_hi = c.smem + SM_A + j * A_CHUNK_BYTES + c.m * 128;
-      const int u = (2 * c.s + (i & 1)) ^ (c.m & 7);
-      *reinterpret_cast<uint4*>(row_hi + u * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(row_hi + 8192 + u * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      // relu -> fp16 hi/lo -> the two 16-byte units of the swizzled A tile (row m, unit 2s+h of chunk j)
+      uint4 vhi, vlo;
+      split_relu2(y[0], y[1], vhi.x, vlo.x);
+      split_relu2(y[2], y[3], vhi.y, vlo.y);
+      split_relu2(y[4], y[5], vhi.z, vlo.z);
+      split_relu2(y[6], y[7], vhi.w, vlo.w);
+      st_shared_v4(unit, vhi);
+      st_shared_v4(unit + 8192, vlo);
       if (i & 1) {
         // this warp's slice of A chunk j is complete: publish it to the tensor core of the pair
         fence_proxy_async();
@@ -250,8 +344,7 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field_tc(const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
@@ -266,7 +359,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       mbar_init(bar_base + (BAR_B_PEER + i) * 8, 1);
       mbar_init(bar_base + (BAR_B_EMPTY + i) * 8, 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(bar_base + (BAR_A_FULL + i) * 8, 16);  // 8 warps x 2 CTAs per chunk
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(bar_base + (BAR_A_FULL + i) * 8, 16);  // 8 warps x 2 CTAs per chunk
+      mbar_init(bar_base + (BAR_A_FREE + i) * 8, 1);
+    }
     mbar_init(bar_base + BAR_F_FULL * 8, 2 * NWORKER_WARPS);
     mbar_init(bar_base + BAR_ACC * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -292,6 +388,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     // =============================== worker warps ===============================
     WorkerCtx c;
     c.smem = smem;
+    c.smem_u = smem_u32(smem);
     c.lane = lane;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     c.s = warp >> 2;                 // 0..3: which 16 columns of every chunk
@@ -308,6 +405,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     float* out_part = reinterpret_cast<float*>(smem + SM_PART);
     const uint32_t acc_bar = bar_base + BAR_ACC * 8;
     uint32_t acc_phase = 0;
+    uint32_t fc_idx = 0;   // number of fc layers whose A operand has been produced so far
     const int grow = threadIdx.x & 63;   // row handled in the geometry stage
     const int gsub = threadIdx.x >> 6;   // 0..7: which 6 of the 48 input channels
 
@@ -359,23 +457,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         }
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
-          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, v, nullptr, nullptr, acc_bar,
-                                acc_phase, 100 + blk);  // X ready (lin_in or fc_1 of blk-1)
+          if (blk == 0) {
+            // X ready (lin_in) and the A buffer is free: stage this block's gather in it
+            mbar_wait_timed(acc_bar, acc_phase, p.status, 100 + blk, t_acc);
+            tc_fence_after();
+            stage_gather(smem, c.smem_u, p.proj + (size_t)blk * map_stride, warp, lane);
+          } else {
+            // fc_1 of block blk-1 is still running: stage chunk by chunk as the tensor core releases them
+            const uint32_t free_par = (fc_idx - 1) & 1;   // phase of the fc layer consuming the chunks produced last
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = chunk_order(jj);
+              mbar_wait(bar_base + (BAR_A_FREE + j) * 8, free_par, p.status, 140 + j);
+              stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, j, warp, lane);
+            }
+            mbar_wait_timed(acc_bar, acc_phase, p.status, 100 + blk, t_acc);   // X ready (fc_1 of blk-1)
+            tc_fence_after();
+          }
+          workers_sync();
+          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, nullptr, v, nullptr, nullptr, acc_bar, acc_phase, 100 + blk);
           acc_phase ^= 1;
+          ++fc_idx;
           epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_bar, acc_phase,
                                 110 + blk);             // H ready
           acc_phase ^= 1;
+          ++fc_idx;
         }
         epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr, acc_bar, acc_phase, 120);
         acc_phase ^= 1;
+        if (v == NS - 1) ++fc_idx;
       }
       // ---- blocks 3..4 on the view-averaged rows ----
       epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 130);
       acc_phase ^= 1;
+      ++fc_idx;
       epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 131);
       acc_phase ^= 1;
+      ++fc_idx;
       epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 132);
       acc_phase ^= 1;
+      ++fc_idx;
       epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part, acc_bar, acc_phase, 133);
       acc_phase ^= 1;
       tc_fence_before();
@@ -472,6 +592,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
               ++seq;
             }
           }
+          if (!lin_in) {
+            if (issuer) umma_commit_pair(bar_base + (BAR_A_FREE + j) * 8);   // chunk j may be overwritten (early gather staging)
+            __syncwarp();
+          }
         }
         if (lin_in) f_phase ^= 1; else a_phase ^= 1;
         if (issuer) umma_commit_pair(bar_base + BAR_ACC * 8);
@@ -516,6 +640,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       uint32_t seq = 0;
       long long t_empty = 0;
       const uint32_t b_base = smem_u32(smem + SM_B);
+      // (a bulk copy cannot complete on a barrier of another CTA than its destination -- tried, it faults -- so each
+      //  CTA streams its own half and the peer forwards "landed" to the leader)
       auto stream_slot = [&](int slot_index) {
         const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
         mbar_wait_timed(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl, t_empty);

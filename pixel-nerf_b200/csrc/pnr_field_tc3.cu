@@ -128,7 +128,7 @@ template <int MODE>
 __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
                                          const uint32_t* off, const float* wt, int view, float* __restrict__ scratch,
-                                         uint32_t pos_base, uint32_t acc_phase, int tag, long long& t_acc) {
+                                         uint32_t pos_base, uint32_t acc_phase, int tag, long long& t_acc, long long& t_free) {
   float4 g[8];      // gather taps of the CURRENT step; refilled for the next step right after use
   float4 bb[2][2];
   uint32_t raw[8];
@@ -212,8 +212,8 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
       const uint32_t slot_l = pos_l % NA, slot_r = pos_r % NA;
       if (h == 0) {
         // both CTAs must have consumed the previous occupants of the two slots
-        mbar_wait(c.bar_base + (BAR_F + slot_l) * 8, ((pos_l / NA) + 1) & 1, p.status, 500 + slot_l);
-        mbar_wait(c.bar_base + (BAR_F + slot_r) * 8, ((pos_r / NA) + 1) & 1, p.status, 510 + slot_r);
+        mbar_wait_timed(c.bar_base + (BAR_F + slot_l) * 8, ((pos_l / NA) + 1) & 1, p.status, 500 + slot_l, t_free);
+        mbar_wait_timed(c.bar_base + (BAR_F + slot_r) * 8, ((pos_r / NA) + 1) & 1, p.status, 510 + slot_r, t_free);
       }
       uint4 vhi, vlo;
       split_relu2(y[0], y[1], vhi.x, vlo.x);
@@ -351,29 +351,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
           epilogue<MODE_GATHER>(c, p, X_COL, nullptr, p.proj + (size_t)blk * map_stride, off, wt, v, nullptr, pos,
-                                acc_phase, 100 + blk, t_acc);   // X ready -> A of fc_0
+                                acc_phase, 100 + blk, t_acc, t_free);   // X ready -> A of fc_0
           acc_phase ^= 1;
           pos += 8;
           epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, off, wt, v, nullptr, pos, acc_phase,
-                                110 + blk, t_acc);              // H ready -> A of fc_1
+                                110 + blk, t_acc, t_free);              // H ready -> A of fc_1
           acc_phase ^= 1;
           pos += 8;
         }
-        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, off, wt, v, scratch, pos, acc_phase, 120, t_acc);
+        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, off, wt, v, scratch, pos, acc_phase, 120, t_acc, t_free);
         acc_phase ^= 1;
       }
       pos += 8;  // fc_0 of block 3 consumed what the last view's COMBINE produced
       // ---- blocks 3..4 on the view-averaged rows ----
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 130, t_acc);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 130, t_acc, t_free);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 131, t_acc);
+      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 131, t_acc, t_free);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 132, t_acc);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 132, t_acc, t_free);
       acc_phase ^= 1;
       pos += 8;
-      epilogue<MODE_FINAL>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 133, t_acc);
+      epilogue<MODE_FINAL>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, nullptr, nullptr, 0, nullptr, pos, acc_phase, 133, t_acc, t_free);
       acc_phase ^= 1;
       pos += 8;
       // ---- lin_out accumulator (16 columns at H_COL): sigmoid rgb / relu sigma (models.py:260-264) ----

@@ -61,9 +61,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* st
 
 // wait and add the stalled cycles to a per-thread counter (debug breakdown, see pnr_tc_counters)
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int* status, int tag, long long& acc) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  mbar_wait_slow(bar, parity, status, tag);
+  const long long t0 = clock64();   // the first try_wait may already sleep (suspend-time hint), so time it too
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, status, tag);
   acc += clock64() - t0;
 }
 
