@@ -46,6 +46,25 @@ WORKLOAD = "c2"
 METRIC = "rays/sec (64c+32f samples, 2 src views)"
 
 
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this same command
+    (profiles/r1_final_k_field_tc.txt); None if the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_final_k_field_tc.txt")
+    if not os.path.exists(p):
+        return None
+    rd = wr = None
+    n = 0
+    tot = 0.0
+    for line in open(p):
+        if "dram__bytes_read.sum [" in line or "dram__bytes_write.sum [" in line:
+            unit = line.split("[")[1].split("]")[0]
+            val = float(line.split("=")[1])
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+            tot += val * mult
+            n += 1
+    return tot / (n / 2) if n else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -244,7 +263,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": n_rays * 4 * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": kern_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (kern_tflops / peak) if kern_tflops else None, "traffic": None,
+                         "frac": (kern_tflops / peak) if kern_tflops else None, "traffic": profiled_traffic(),
                          "peak_source": peak_src, "kernel_launches": int(kern_launches),
                          "kernel_ms_per_step": kern_ms / args.steps,
                          "note": "algorithmic fp32-model FLOPs of the reference (SURVEY 8d) / device time of the "

@@ -544,9 +544,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         for (int jj = 0; jj < nchunks; ++jj) {
           const int j = lin_in ? 0 : chunk_order(jj);
           if (lin_in) {
-            mbar_wait_timed(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
+            mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
           } else {
-            mbar_wait_timed(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, t_afull);
+            mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, t_afull);
           }
           const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
           const uint64_t a_lo = a_hi + (8192 >> 4);
@@ -556,8 +556,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
             // ---- W_hi slot: D += Ahi*Whi + Alo*Whi ----
             {
               const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-              mbar_wait_timed(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
-              mbar_wait_timed(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+              mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+              mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
               tc_fence_after();
               const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
               if (issuer) {
@@ -577,8 +577,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
             // ---- W_lo slot: D += Ahi*Wlo ----
             {
               const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-              mbar_wait_timed(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
-              mbar_wait_timed(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+              mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+              mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
               tc_fence_after();
               const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
               if (issuer) {
@@ -624,11 +624,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     } else if (lane == 0) {
       // ============ peer CTA: forward "my half of the weight slot landed" to the leader ============
       uint32_t seq = 0;
+      long long t_fwd = 0;
       const uint32_t per_tile = (uint32_t)NS * (SLOTS_LIN_IN + 6 * SLOTS_FC) + 4 * SLOTS_FC;
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
         for (uint32_t i = 0; i < per_tile; ++i) {
           const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-          mbar_wait(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl);
+          mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl, t_fwd);
           mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
           ++seq;
         }
@@ -644,7 +645,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       //  CTA streams its own half and the peer forwards "landed" to the leader)
       auto stream_slot = [&](int slot_index) {
         const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-        mbar_wait_timed(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl, t_empty);
+        mbar_wait_spin(bar_base + (BAR_B_EMPTY + sl) * 8, ph ^ 1, p.status, 400 + sl, t_empty);
         const uint32_t full = bar_base + (BAR_B_FULL + sl) * 8;
         mbar_expect_tx(full, SLOT_BYTES);
         bulk_g2s(b_base + sl * SLOT_BYTES, slots + (size_t)slot_index * SLOT_BYTES, SLOT_BYTES, full);

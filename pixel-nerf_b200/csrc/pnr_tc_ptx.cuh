@@ -54,6 +54,33 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
     }
   }
 }
+// Latency-critical single waiters (MMA issuer, weight streamer, forwarder) spin without the suspend hint: a parked
+// warp wakes up noticeably later than a spinning one, and these few threads cost no meaningful issue bandwidth.
+__device__ __forceinline__ uint32_t mbar_try_wait_nohint(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int* status, int tag, long long& acc) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      if (*(volatile int*)status != 0) break;
+      if (clock64() - t0 > TIMEOUT_CYCLES) {
+        atomicCAS(status, 0, tag);
+        break;
+      }
+    }
+  }
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, status, tag);
