@@ -65,6 +65,15 @@ def profiled_traffic():
     return tot / (n / 2) if n else None
 
 
+def profiled_tensor_active():
+    """ncu sm__pipe_tensor_cycles_active (% of peak, mean over the captured launches) from the same capture."""
+    p = os.path.join(ROOT, "profiles", "r1_final_k_field_tc.txt")
+    if not os.path.exists(p):
+        return None
+    vals = [float(l.split("=")[1]) for l in open(p) if "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed" in l]
+    return sum(vals) / len(vals) if vals else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -265,6 +274,9 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": kern_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": (kern_tflops / peak) if kern_tflops else None, "traffic": profiled_traffic(),
                          "peak_source": peak_src, "kernel_launches": int(kern_launches),
+                         "ncu_tensor_pipe_active_pct": profiled_tensor_active(),
+                         "traffic_note": "dram bytes per launch from profiles/r1_final_k_field_tc.txt (same command under ncu); "
+                                         "dominated by the write-back / refetch caused by the 256 MB L2 flush between steps",
                          "kernel_ms_per_step": kern_ms / args.steps,
                          "note": "algorithmic fp32-model FLOPs of the reference (SURVEY 8d) / device time of the "
                                  "MLP-contraction kernel(s), CUDA events on the launch stream"},
