@@ -100,6 +100,7 @@ struct Params {
   int64_t total_points;
   int64_t n_tiles;
   int* status;
+  int spin_acc;    // experiment (PNR_TC2_SPIN_ACC=1): workers spin on the accumulator barrier instead of parking
 };
 
 using namespace tcptx;
@@ -167,45 +168,12 @@ __device__ __forceinline__ uint32_t a_unit_offset(int j, int m, int u) {
   return (uint32_t)(SM_A + j * A_CHUNK_BYTES + m * 128 + ((u ^ (m & 7)) * 16));
 }
 
-// Coalesced gather of the projected-latent map for one ResNet block: G[row][:] = sum_k w_k * P_i[tap_k(row)][:].
-// A warp takes one row at a time and its 32 lanes read 512 contiguous bytes per tap (4 wavefronts per load instead of
-// the 32 a lane-per-row gather costs); the result is parked in the (currently free) A-operand buffer, in exactly the
-// two 16-byte slots that the thread owning (row, 8 features) overwrites with its fp16 hi/lo units later.
-__device__ __forceinline__ void stage_gather(uint8_t* smem, uint32_t smem_u, const float* __restrict__ proj_i, int warp,
-                                             int lane) {
-  const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
-  float4 t[4], tn[4];
-  // 64 rows / 16 warps = 4 rows per warp, 4 spans of 128 features per row
-  auto issue = [&](float4* dst, int it) {
-    const int row = warp * 4 + (it >> 2), sp = it & 3;
-    const uint32_t* geo = geo_all + row * 8;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + sp * 128) + lane);
-  };
-  issue(t, 0);
-#pragma unroll 1
-  for (int it = 0; it < 16; ++it) {
-    if (it + 1 < 16) issue(tn, it + 1);
-    const int row = warp * 4 + (it >> 2), sp = it & 3;
-    const uint32_t* geo = geo_all + row * 8;
-    const float w0 = __uint_as_float(geo[4]), w1 = __uint_as_float(geo[5]), w2 = __uint_as_float(geo[6]),
-                w3 = __uint_as_float(geo[7]);
-    float4 g;
-    g.x = ((t[0].x * w0 + t[1].x * w1) + t[2].x * w2) + t[3].x * w3;
-    g.y = ((t[0].y * w0 + t[1].y * w1) + t[2].y * w2) + t[3].y * w3;
-    g.z = ((t[0].z * w0 + t[1].z * w1) + t[2].z * w2) + t[3].z * w3;
-    g.w = ((t[0].w * w0 + t[1].w * w1) + t[2].w * w2) + t[3].w * w3;
-    // lane -> features [sp*128 + 4*lane, +4): chunk j = 2*sp + lane/16, unit u = (lane%16)/2, hi slot if lane even
-    const int j = 2 * sp + (lane >> 4), u = (lane & 15) >> 1;
-    st_shared_f4(smem_u + a_unit_offset(j, row, u) + ((lane & 1) ? 8192u : 0u), g);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = tn[k];
-  }
-}
-
-// The same for ONE k-chunk (64 features) of all 64 rows: 16 lanes cover a row's 64 features, a warp-load fetches two
-// rows.  Used to stage the next block's gather chunk by chunk while the tensor core is still consuming the rest of
-// the A buffer.
+// Coalesced gather of the projected-latent map: G[row][:] = sum_k w_k * P_i[tap_k(row)][:].  A warp-load covers two
+// rows x 64 features with lane = feature (2 x 256 contiguous bytes per tap instead of the 32 scattered lines a
+// lane-per-row gather costs); the result is parked in the (free) A-operand buffer, in exactly the two 16-byte slots
+// that the thread owning (row, 8 features) overwrites with its fp16 hi/lo units later.
+// One k-chunk (64 features) of all 64 rows; staged chunk by chunk so that it can run while the tensor core is still
+// consuming the rest of the A buffer.
 __device__ __forceinline__ void stage_gather_chunk(uint8_t* smem, uint32_t smem_u, const float* __restrict__ proj_i,
                                                    int j, int warp, int lane) {
   const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
@@ -244,7 +212,8 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
   if (MODE == MODE_GATHER) {
     // the accumulator barrier was already passed by the caller (the gather had to be staged after it)
   } else {
-    mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
+    if (p.spin_acc) mbar_wait_spin(acc_bar, acc_phase, p.status, tag, *c.t_acc);
+    else mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
     tc_fence_after();
   }
   tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, 0), raw);
@@ -458,10 +427,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
           if (blk == 0) {
-            // X ready (lin_in) and the A buffer is free: stage this block's gather in it
+            // lin_in only reads chunk 0 (the 42 input channels): stage the gather into chunks 1..7 while it runs,
+            // chunk 0 once X is ready
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = chunk_order(jj);
+              if (j != 0) stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, j, warp, lane);
+            }
             mbar_wait_timed(acc_bar, acc_phase, p.status, 100 + blk, t_acc);
             tc_fence_after();
-            stage_gather(smem, c.smem_u, p.proj + (size_t)blk * map_stride, warp, lane);
+            stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, 0, warp, lane);
           } else {
             // fc_1 of block blk-1 is still running: stage chunk by chunk as the tensor core releases them
             const uint32_t free_par = (fc_idx - 1) & 1;   // phase of the fc layer consuming the chunks produced last
@@ -796,6 +770,10 @@ int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, cons
   p.out = out;
   p.total_points = total_points;
   p.n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+  {
+    const char* e = getenv("PNR_TC2_SPIN_ACC");
+    p.spin_acc = (e && e[0] == '1') ? 1 : 0;
+  }
   int rc = tc::get_status_buffer(&p.status);
   if (rc) return rc;
   const int pairs = tc_pairs(p.n_tiles);

@@ -92,3 +92,41 @@ def test_sharded_render_matches_single_gpu_order():
         second = renderer._forward_fused(rep.net, rays[:, 257:].to("cuda:1"), False,
                                          noise_in={k: v[257:].contiguous().cuda(1) for k, v in noise.items()}).fine.rgb
     assert torch.equal(second.cpu(), whole[:, 257:].cpu())
+
+
+@pytest.mark.parametrize("SB,NS", [(2, 2), (1, 6), (3, 1)])
+def test_tensor_engine_multi_object_and_many_views(SB, NS):
+    """Super-batches (train.py uses SB=4) and the C5 sweep's NS=6: tensor engine vs SIMT engine on synthetic
+    latents, per-object focal lengths, through NeRFRenderer's fused path."""
+    import gpu_util
+    import golden_util as gu
+    from model import make_model
+    from render import NeRFRenderer
+    import pnr_native as pn
+    dev = torch.device("cuda:0")
+    W = H = 32
+    net = make_model(gpu_util.model_conf(512))
+    net.mlp_coarse.load_state_dict(gu.synth.make_mlp_weights(21, 512))
+    net.mlp_fine.load_state_dict(gu.synth.make_mlp_weights(22, 512))
+    net = net.to(dev).eval()
+    latent = gu.synth.make_latent(7, SB * NS, 16, 16).to(dev)
+    poses = torch.stack([torch.stack([gu.synth.pose_spherical(40.0 * v + 25.0 * o, -30.0, 1.3) for v in range(NS)])
+                         for o in range(SB)]).to(dev)
+    focal = torch.linspace(30.0, 36.0, SB).to(dev)          # one focal length per object
+    net.set_scene(latent, poses, focal, None, W, H)
+    renderer = NeRFRenderer(n_coarse=32, n_fine=16, n_fine_depth=8, white_bkgd=True).eval()
+    B = 200
+    tgt = torch.stack([gu.synth.pose_spherical(100.0 + 50.0 * o, -15.0, 1.3) for o in range(SB)])
+    rays = gu.synth.gen_rays(tgt, W, H, 32.0, 0.8, 1.8).reshape(SB, -1, 8)[:, :B].contiguous().to(dev)
+    noise = {k: v.to(dev) for k, v in gu.synth.draw_noise(4, SB * B, 32, 16, 8).items()}
+    with torch.no_grad():
+        net.engine = "tc"
+        a = renderer._forward_fused(net, rays, True, noise_in=noise, want_z=True)
+        assert pn.tc_status() == 0
+        net.engine = "simt"
+        b = renderer._forward_fused(net, rays, True, noise_in=noise, want_z=True)
+    assert a.fine.rgb.shape == (SB, B, 3)
+    assert (a.coarse.rgb - b.coarse.rgb).abs().max() < 1e-4
+    flipped = ((a.fine.z - b.fine.z).abs() > 2e-4).any(dim=-1)
+    assert flipped.float().mean() < 0.05
+    assert (a.fine.rgb[~flipped] - b.fine.rgb[~flipped]).abs().max() < 1e-4
