@@ -184,7 +184,8 @@ int pnr_profile_end(double* total_ms, int64_t* launches);
 /* Debug / test hook for the tensor engine: synchronises the current device and returns its
  * status word (0 = ok, otherwise the tag of the first barrier wait that timed out), then clears it. */
 int pnr_tc_status(int* status);
-/* Debug: per-role stall-cycle counters of the tensor engine (8 values, see csrc/pnr_field_tc.cu); clears them. */
+/* Debug: per-role stall-cycle counters of the tensor engine (8 values, documented at pnr_tc_counters in
+ * csrc/pnr_field_tc.cu); synchronises the device and clears them. */
 int pnr_tc_counters(unsigned long long* out8);
 
 #ifdef __cplusplus

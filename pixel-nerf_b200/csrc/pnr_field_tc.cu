@@ -87,6 +87,7 @@ constexpr int BAR_F_FULL = BAR_A_FREE + 8;
 constexpr int BAR_ACC = BAR_F_FULL + 1;
 constexpr int BAR_COUNT = BAR_ACC + 1;
 constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
+constexpr int SM_TSTAMP = SM_TMEM_PTR + 8;   // debug: clock64 of the last accumulator commit (leader CTA)
 
 
 struct Params {
@@ -116,6 +117,7 @@ struct WorkerCtx {
   int lane, s, m, n_hi;
   float w_scale, w_inv;
   long long* t_acc;     // cycles spent waiting for the accumulator barrier
+  long long* dbg;       // [0] commit -> worker passes the barrier, [1] barrier -> first wave published (MODE_HIDDEN)
 };
 
 // A worker thread owns row m and 8 "steps" of 8 features per layer:
@@ -216,6 +218,8 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
     else mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
     tc_fence_after();
   }
+  const long long t_pass = clock64();
+  if (MODE == MODE_HIDDEN) c.dbg[0] += t_pass - *reinterpret_cast<volatile long long*>(c.smem + SM_TSTAMP);
   tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, 0), raw);
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   const int NS = p.sc.NS;
@@ -303,6 +307,7 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
         tc_fence_before();
         __syncwarp();
         if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
+        if (MODE == MODE_HIDDEN && i == 1) c.dbg[1] += clock64() - t_pass;
       }
     }
   }
@@ -368,6 +373,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.w_scale = w_scale;
     c.w_inv = w_inv;
     long long t_acc = 0, t_geo = 0;
+    long long dbg[2] = {0, 0};
+    c.dbg = dbg;
     c.t_acc = &t_acc;
     const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
@@ -498,9 +505,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     }
     if (threadIdx.x == 0) {
       unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p.status + 2);
-      atomicAdd(cnt + 4, (unsigned long long)(clock64() - t_wstart));
-      atomicAdd(cnt + 5, (unsigned long long)t_acc);
-      atomicAdd(cnt + 6, (unsigned long long)t_geo);
+      if (rank == 0) {
+        atomicAdd(cnt + 4, (unsigned long long)dbg[0]);
+        atomicAdd(cnt + 5, (unsigned long long)dbg[1]);
+      }
+
     }
   } else if (warp == WARP_MMA) {
     if (rank == 0) {
@@ -509,7 +518,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       // tcgen05.mma / tcgen05.commit instructions themselves are predicated on one elected lane.
       uint32_t seq = 0;          // weight-slot sequence number
       uint32_t a_phase = 0, f_phase = 0;
-      long long t_afull = 0, t_bfull = 0, t_bpeer = 0;
+      long long t_afull = 0, t_alater = 0, t_bfull = 0, t_bpeer = 0;
       const long long t_start = clock64();
       const uint32_t a_base = smem_u32(smem + SM_A), b_base = smem_u32(smem + SM_B);
       const uint64_t desc0 = make_desc(0);   // address field is added per operand (16-byte units)
@@ -520,7 +529,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           if (lin_in) {
             mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
           } else {
-            mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, t_afull);
+            mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, jj == 0 ? t_afull : t_alater);
           }
           const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
           const uint64_t a_lo = a_hi + (8192 >> 4);
@@ -572,7 +581,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           }
         }
         if (lin_in) f_phase ^= 1; else a_phase ^= 1;
-        if (issuer) umma_commit_pair(bar_base + BAR_ACC * 8);
+        if (issuer) {
+          umma_commit_pair(bar_base + BAR_ACC * 8);
+          *reinterpret_cast<volatile long long*>(smem + SM_TSTAMP) = clock64();
+        }
         __syncwarp();
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
@@ -594,6 +606,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         atomicAdd(cnt + 1, (unsigned long long)t_afull);
         atomicAdd(cnt + 2, (unsigned long long)t_bfull);
         atomicAdd(cnt + 3, (unsigned long long)t_bpeer);
+        atomicAdd(cnt + 6, (unsigned long long)t_alater);
       }
     } else if (lane == 0) {
       // ============ peer CTA: forward "my half of the weight slot landed" to the leader ============
@@ -886,9 +899,11 @@ int pnr_tc_status(int* out) {
 }
 
 
-// Debug: cycle breakdown accumulated over all launches since the last call (summed over clusters):
-// [0] MMA thread total, [1] MMA waits for A chunks, [2] for its own weight slot, [3] for the peer's slot,
-// [4] worker total, [5] worker waits for the accumulator, [6] geometry stage, [7] streamer waits for a free slot.
+// Debug: cycle breakdown accumulated over all launches since the last call (summed over the leader CTAs):
+// [0] MMA warp total, [1] its waits for the FIRST A chunk of a layer (layer-boundary bubble), [2] for its own weight
+// slot, [3] for the peer's slot, [4] hidden-layer epilogues: accumulator commit -> workers past the barrier,
+// [5] barrier -> first wave of A chunks published, [6] MMA waits for later A chunks, [7] streamer waits for a free slot.
+// (M-split variant; the N-split variant fills [0] total, [1] chunk waits, [2] weight waits, [4..6] worker totals.)
 int pnr_tc_counters(unsigned long long* out8) {
   int* buf = nullptr;
   int rc = tc::get_status_buffer(&buf);
