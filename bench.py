@@ -269,7 +269,7 @@ def run_ours(args):
                        "rays_per_step_per_gpu": n_rays, "engine": args.engine, "l2_flush_between_steps": True,
                        "parallelism": f"ray-sharded x{world}", "flop_per_ray": fl},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 8 * 4 * world,
-                    "d2h_bytes_per_step": n_rays * 4 * 4},
+                    "d2h_bytes_per_step": n_rays * 4 * 4 * world},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": kern_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": (kern_tflops / peak) if kern_tflops else None, "traffic": profiled_traffic(),

@@ -1,5 +1,5 @@
 import sys, os, torch
-sys.path.insert(0, 'tests'); sys.path.insert(0, 'pixel-nerf_b200/src')
+sys.path.insert(0, "tests"); sys.path.insert(0, "pixel-nerf_b200/src")
 import golden_util as gu, gpu_util, pnr_native as pn
 case = gu.load_case("c3_small")
 cfg = case["cfg"]
