@@ -84,8 +84,8 @@ constexpr int BAR_B_EMPTY = BAR_B_PEER + NSLOTS;  // [NSLOTS]
 constexpr int BAR_A_FULL = BAR_B_EMPTY + NSLOTS;  // [8]
 constexpr int BAR_A_FREE = BAR_A_FULL + 8;         // [8] chunk consumed by the MMA of the current fc layer
 constexpr int BAR_F_FULL = BAR_A_FREE + 8;
-constexpr int BAR_ACC = BAR_F_FULL + 1;
-constexpr int BAR_COUNT = BAR_ACC + 1;
+constexpr int BAR_ACC = BAR_F_FULL + 1;             // [2] accumulator block 0 / block 1 ready
+constexpr int BAR_COUNT = BAR_ACC + 2;
 constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
 constexpr int SM_TSTAMP = SM_TMEM_PTR + 8;   // debug: clock64 of the last accumulator commit (leader CTA)
 
@@ -198,116 +198,141 @@ __device__ __forceinline__ void stage_gather_chunk(uint8_t* smem, uint32_t smem_
   }
 }
 
-// One epilogue pass over this thread's 64 features of one layer (8 steps of 8).  TMEM loads and bias loads of step
-// i+1 are issued before step i is processed; MODE_GATHER reads the staged gather values back from shared memory.
+// One epilogue pass over this thread's 64 features of one layer, in two halves of 4 steps: the MMA warp computes a
+// layer feature-block by feature-block (b = 0: features 0..255, then b = 1), so half 0 (steps 0..3, k-chunks 0..3 of
+// the next layer) runs after BAR_ACC+0 while the tensor core is still busy with block 1, and half 1 after BAR_ACC+1.
+//   gate / free_par : the layer that is still running also reads the A buffer; chunk j may only be overwritten once
+//                     its block-1 pass has consumed it (a_free[j], phase free_par).
+// TMEM loads and bias loads of the next step are issued before the current step is processed; MODE_GATHER reads the
+// staged gather values back from shared memory (staged here as the chunks are released, when gated).
 template <int MODE>
 __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
-                                         int view, float* __restrict__ scratch, float* out_part, uint32_t acc_bar,
-                                         uint32_t acc_phase, int tag) {
+                                         int view, float* __restrict__ scratch, float* out_part, uint32_t acc_phase,
+                                         bool gate, uint32_t free_par, int warp, int tag) {
   float4 bb[2][2];
   uint32_t raw[8];
   if (MODE != MODE_GATHER) {
     bb[0][0] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, 0)));
     bb[0][1] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, 0)) + 1);
   }
-  if (MODE == MODE_GATHER) {
-    // the accumulator barrier was already passed by the caller (the gather had to be staged after it)
-  } else {
-    if (p.spin_acc) mbar_wait_spin(acc_bar, acc_phase, p.status, tag, *c.t_acc);
-    else mbar_wait_timed(acc_bar, acc_phase, p.status, tag, *c.t_acc);
-    tc_fence_after();
-  }
-  const long long t_pass = clock64();
-  if (MODE == MODE_HIDDEN) c.dbg[0] += t_pass - *reinterpret_cast<volatile long long*>(c.smem + SM_TSTAMP);
-  tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, 0), raw);
   float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
   const int NS = p.sc.NS;
   const bool produce = (MODE != MODE_OUT) && !(MODE == MODE_COMBINE && view != NS - 1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int n0 = step_feature(c, i);
-    const uint32_t col = step_tmem_col(c, i);
-    const int j = 4 * (i >> 2) + 2 * c.n_hi + ((i >> 1) & 1);
-    const uint32_t unit = c.smem_u + a_unit_offset(j, c.m, 2 * c.s + (i & 1));
-    float y[8];
-    tmem_ld_wait8(raw);
+  for (int half = 0; half < 2; ++half) {
+    if (MODE == MODE_GATHER && gate && half == 1) {
+      // the tail of the running layer releases chunks 4, 6, 5, 7: stage them before its accumulator barrier
+      for (int jj = 4; jj < 8; ++jj) {
+        const int jf = chunk_order(jj);
+        mbar_wait(c.bar_base + (BAR_A_FREE + jf) * 8, free_par, p.status, 140 + jf);
+        stage_gather_chunk(c.smem, c.smem_u, proj_i, jf, warp, c.lane);
+      }
+      workers_sync();
+    }
+    mbar_wait_timed(c.bar_base + (BAR_ACC + half) * 8, acc_phase, p.status, tag + half, *c.t_acc);
+    tc_fence_after();
+    if (MODE == MODE_GATHER && !gate && half == 0) {
+      // block 0 of a view: chunks 1..7 were staged while lin_in ran; chunk 0 holds lin_in's operand, which BOTH of its
+      // passes read, so wait for the second accumulator barrier as well before overwriting it
+      mbar_wait_timed(c.bar_base + (BAR_ACC + 1) * 8, acc_phase, p.status, tag + 1, *c.t_acc);
+      stage_gather_chunk(c.smem, c.smem_u, proj_i, 0, warp, c.lane);
+      workers_sync();
+    }
+    tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, 4 * half), raw);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(raw[e]) * c.w_inv;
-    if (i + 1 < 8) {
-      tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, i + 1), raw);
-      if (MODE != MODE_GATHER) {
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = 4 * half + ii;
+      const int n0 = step_feature(c, i);
+      const uint32_t col = step_tmem_col(c, i);
+      const int j = 4 * (i >> 2) + 2 * c.n_hi + ((i >> 1) & 1);
+      const uint32_t unit = c.smem_u + a_unit_offset(j, c.m, 2 * c.s + (i & 1));
+      if ((i & 1) == 0 && gate) {
+        if (MODE == MODE_GATHER) {
+          if (half == 0) {
+            const int j0 = ((i >> 1) & 1), j1 = j0 + 2;
+            mbar_wait(c.bar_base + (BAR_A_FREE + j0) * 8, free_par, p.status, 140 + j0);
+            mbar_wait(c.bar_base + (BAR_A_FREE + j1) * 8, free_par, p.status, 140 + j1);
+            stage_gather_chunk(c.smem, c.smem_u, proj_i, j0, warp, c.lane);
+            stage_gather_chunk(c.smem, c.smem_u, proj_i, j1, warp, c.lane);
+            workers_sync();
+          }
+        } else if (produce) {
+          mbar_wait(c.bar_base + (BAR_A_FREE + j) * 8, free_par, p.status, 150 + j);
+        }
+      }
+      float y[8];
+      tmem_ld_wait8(raw);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(raw[e]) * c.w_inv;
+      if (ii + 1 < 4) tmem_ld8_issue(c.tmem + acc_col + step_tmem_col(c, i + 1), raw);
+      if (MODE != MODE_GATHER && i + 1 < 8) {
         bb[(i + 1) & 1][0] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, i + 1)));
         bb[(i + 1) & 1][1] = __ldg(reinterpret_cast<const float4*>(bias + step_feature(c, i + 1)) + 1);
       }
-    }
-    if (MODE == MODE_GATHER) {
-      const float4 g0 = ld_shared_f4(unit), g1 = ld_shared_f4(unit + 8192);
-      y[0] += g0.x; y[1] += g0.y; y[2] += g0.z; y[3] += g0.w;
-      y[4] += g1.x; y[5] += g1.y; y[6] += g1.z; y[7] += g1.w;
-    } else {
-      const float4 b0 = bb[i & 1][0], b1 = bb[i & 1][1];
-      y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
-      y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
-    }
-    if (MODE == MODE_COMBINE && NS > 1) {
-      // multi-view mean (util.combine_interleaved): sum in view order, then divide
-      float* sp = scratch + (size_t)n0 * ROWS + c.m;  // [feature][row]: lanes are contiguous
-      if (view == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
+      if (MODE == MODE_GATHER) {
+        const float4 g0 = ld_shared_f4(unit), g1 = ld_shared_f4(unit + 8192);
+        y[0] += g0.x; y[1] += g0.y; y[2] += g0.z; y[3] += g0.w;
+        y[4] += g1.x; y[5] += g1.y; y[6] += g1.z; y[7] += g1.w;
       } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = sp[e * ROWS] + y[e];
-        if (view < NS - 1) {
+        const float4 b0 = bb[i & 1][0], b1 = bb[i & 1][1];
+        y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+        y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+      }
+      if (MODE == MODE_COMBINE && NS > 1) {
+        float* sp = scratch + (size_t)n0 * ROWS + c.m;
+        if (view == 0) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
         } else {
-          const float ns = (float)NS;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = y[e] / ns;
+          for (int e = 0; e < 8; ++e) y[e] = sp[e * ROWS] + y[e];
+          if (view < NS - 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
+          } else {
+            const float ns = (float)NS;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = y[e] / ns;
+          }
         }
       }
-    }
-    if (MODE == MODE_GATHER || MODE == MODE_BIAS_WB || (MODE == MODE_COMBINE && produce)) {
-      float z[8];
+      if (MODE == MODE_GATHER || MODE == MODE_BIAS_WB || (MODE == MODE_COMBINE && produce)) {
+        float z[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) z[e] = y[e] * c.w_scale;
-      tmem_st8(c.tmem + X_COL + col, z);  // residual stream write-back
-    }
-    if (MODE == MODE_OUT) {
-      // lin_out(relu(x)) partial dot products over this thread's features (resnetfc.py:183)
-      const float* W = p.mlp.lin_out_w + n0;
-#pragma unroll
-      for (int e4 = 0; e4 < 2; ++e4) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + 0 * D) + e4);
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + 1 * D) + e4);
-        const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + 2 * D) + e4);
-        const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + 3 * D) + e4);
-        const float a0 = fmaxf(y[4 * e4 + 0], 0.f), a1 = fmaxf(y[4 * e4 + 1], 0.f);
-        const float a2 = fmaxf(y[4 * e4 + 2], 0.f), a3 = fmaxf(y[4 * e4 + 3], 0.f);
-        o0 = fmaf(a3, w0.w, fmaf(a2, w0.z, fmaf(a1, w0.y, fmaf(a0, w0.x, o0))));
-        o1 = fmaf(a3, w1.w, fmaf(a2, w1.z, fmaf(a1, w1.y, fmaf(a0, w1.x, o1))));
-        o2 = fmaf(a3, w2.w, fmaf(a2, w2.z, fmaf(a1, w2.y, fmaf(a0, w2.x, o2))));
-        o3 = fmaf(a3, w3.w, fmaf(a2, w3.z, fmaf(a1, w3.y, fmaf(a0, w3.x, o3))));
+        for (int e = 0; e < 8; ++e) z[e] = y[e] * c.w_scale;
+        tmem_st8(c.tmem + X_COL + col, z);
       }
-    } else if (produce) {
-      // relu -> fp16 hi/lo -> the two 16-byte units of the swizzled A tile (row m, unit 2s+h of chunk j)
-      uint4 vhi, vlo;
-      split_relu2(y[0], y[1], vhi.x, vlo.x);
-      split_relu2(y[2], y[3], vhi.y, vlo.y);
-      split_relu2(y[4], y[5], vhi.z, vlo.z);
-      split_relu2(y[6], y[7], vhi.w, vlo.w);
-      st_shared_v4(unit, vhi);
-      st_shared_v4(unit + 8192, vlo);
-      if (i & 1) {
-        // this warp's slice of A chunk j is complete: publish it to the tensor core of the pair
-        fence_proxy_async();
-        if (MODE != MODE_HIDDEN) tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
-        if (MODE == MODE_HIDDEN && i == 1) c.dbg[1] += clock64() - t_pass;
+      if (MODE == MODE_OUT) {
+        const float* W = p.mlp.lin_out_w + n0;
+#pragma unroll
+        for (int e4 = 0; e4 < 2; ++e4) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + 0 * D) + e4);
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + 1 * D) + e4);
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + 2 * D) + e4);
+          const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + 3 * D) + e4);
+          const float a0 = fmaxf(y[4 * e4 + 0], 0.f), a1 = fmaxf(y[4 * e4 + 1], 0.f);
+          const float a2 = fmaxf(y[4 * e4 + 2], 0.f), a3 = fmaxf(y[4 * e4 + 3], 0.f);
+          o0 = fmaf(a3, w0.w, fmaf(a2, w0.z, fmaf(a1, w0.y, fmaf(a0, w0.x, o0))));
+          o1 = fmaf(a3, w1.w, fmaf(a2, w1.z, fmaf(a1, w1.y, fmaf(a0, w1.x, o1))));
+          o2 = fmaf(a3, w2.w, fmaf(a2, w2.z, fmaf(a1, w2.y, fmaf(a0, w2.x, o2))));
+          o3 = fmaf(a3, w3.w, fmaf(a2, w3.z, fmaf(a1, w3.y, fmaf(a0, w3.x, o3))));
+        }
+      } else if (produce) {
+        uint4 vhi, vlo;
+        split_relu2(y[0], y[1], vhi.x, vlo.x);
+        split_relu2(y[2], y[3], vhi.y, vlo.y);
+        split_relu2(y[4], y[5], vhi.z, vlo.z);
+        split_relu2(y[6], y[7], vhi.w, vlo.w);
+        st_shared_v4(unit, vhi);
+        st_shared_v4(unit + 8192, vlo);
+        if (i & 1) {
+          fence_proxy_async();
+          if (MODE != MODE_HIDDEN) tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (c.lane == 0) mbar_arrive_cta(c.bar_base + (BAR_A_FULL + j) * 8, 0);
+        }
       }
     }
   }
@@ -338,7 +363,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       mbar_init(bar_base + (BAR_A_FREE + i) * 8, 1);
     }
     mbar_init(bar_base + BAR_F_FULL * 8, 2 * NWORKER_WARPS);
-    mbar_init(bar_base + BAR_ACC * 8, 1);
+    mbar_init(bar_base + (BAR_ACC + 0) * 8, 1);
+    mbar_init(bar_base + (BAR_ACC + 1) * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -379,7 +405,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
     float* out_part = reinterpret_cast<float*>(smem + SM_PART);
-    const uint32_t acc_bar = bar_base + BAR_ACC * 8;
     uint32_t acc_phase = 0;
     uint32_t fc_idx = 0;   // number of fc layers whose A operand has been produced so far
     const int grow = threadIdx.x & 63;   // row handled in the geometry stage
@@ -433,51 +458,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         }
         // ---- lin_in, then blocks 0..2 ----
         for (int blk = 0; blk < 3; ++blk) {
+          const float* proj_blk = p.proj + (size_t)blk * map_stride;
           if (blk == 0) {
-            // lin_in only reads chunk 0 (the 42 input channels): stage the gather into chunks 1..7 while it runs,
-            // chunk 0 once X is ready
-            for (int jj = 0; jj < 8; ++jj) {
-              const int j = chunk_order(jj);
-              if (j != 0) stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, j, warp, lane);
-            }
-            mbar_wait_timed(acc_bar, acc_phase, p.status, 100 + blk, t_acc);
-            tc_fence_after();
-            stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, 0, warp, lane);
-          } else {
-            // fc_1 of block blk-1 is still running: stage chunk by chunk as the tensor core releases them
-            const uint32_t free_par = (fc_idx - 1) & 1;   // phase of the fc layer consuming the chunks produced last
-            for (int jj = 0; jj < 8; ++jj) {
-              const int j = chunk_order(jj);
-              mbar_wait(bar_base + (BAR_A_FREE + j) * 8, free_par, p.status, 140 + j);
-              stage_gather_chunk(smem, c.smem_u, p.proj + (size_t)blk * map_stride, j, warp, lane);
-            }
-            mbar_wait_timed(acc_bar, acc_phase, p.status, 100 + blk, t_acc);   // X ready (fc_1 of blk-1)
-            tc_fence_after();
+            for (int jj = 1; jj < 8; ++jj) stage_gather_chunk(smem, c.smem_u, proj_blk, chunk_order(jj), warp, lane);
           }
-          workers_sync();
-          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, nullptr, v, nullptr, nullptr, acc_bar, acc_phase, 100 + blk);
+          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, proj_blk, v, nullptr, nullptr, acc_phase, blk != 0,
+                                (fc_idx - 1) & 1, warp, 100 + 2 * blk);
           acc_phase ^= 1;
           ++fc_idx;
-          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_bar, acc_phase,
-                                110 + blk);             // H ready
+          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_phase, true,
+                                (fc_idx - 1) & 1, warp, 110 + 2 * blk);
           acc_phase ^= 1;
           ++fc_idx;
         }
-        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr, acc_bar, acc_phase, 120);
+        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr, acc_phase, true,
+                               (fc_idx - 1) & 1, warp, 120);
         acc_phase ^= 1;
         if (v == NS - 1) ++fc_idx;
       }
-      // ---- blocks 3..4 on the view-averaged rows ----
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 130);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                            (fc_idx - 1) & 1, warp, 130);
       acc_phase ^= 1;
       ++fc_idx;
-      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 131);
+      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                             (fc_idx - 1) & 1, warp, 132);
       acc_phase ^= 1;
       ++fc_idx;
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_bar, acc_phase, 132);
+      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                            (fc_idx - 1) & 1, warp, 134);
       acc_phase ^= 1;
       ++fc_idx;
-      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part, acc_bar, acc_phase, 133);
+      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part, acc_phase, false, 0, warp, 136);
       acc_phase ^= 1;
       tc_fence_before();
       workers_sync();
@@ -524,19 +535,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       const uint64_t desc0 = make_desc(0);   // address field is added per operand (16-byte units)
       const bool issuer = elect_one();
       auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
-        for (int jj = 0; jj < nchunks; ++jj) {
-          const int j = lin_in ? 0 : chunk_order(jj);
-          if (lin_in) {
-            mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
-          } else {
-            mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, jj == 0 ? t_afull : t_alater);
-          }
-          const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
-          const uint64_t a_lo = a_hi + (8192 >> 4);
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const uint32_t d = tmem_base + dcol + b * 128;
-            // ---- W_hi slot: D += Ahi*Whi + Alo*Whi ----
+        // feature-block outer: all k-chunks for output features 0..255, then 256..511, so that the epilogue of
+        // block 0 overlaps the MMAs of block 1 and the next layer can start without a bubble (the A chunks are
+        // waited for in the first pass only; the second pass releases them chunk by chunk)
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+          const uint32_t d = tmem_base + dcol + b * 128;
+          for (int jj = 0; jj < nchunks; ++jj) {
+            const int j = lin_in ? 0 : chunk_order(jj);
+            if (b == 0) {
+              if (lin_in) {
+                mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
+              } else {
+                mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, jj == 0 ? t_afull : t_alater);
+              }
+            }
+            const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
+            const uint64_t a_lo = a_hi + (8192 >> 4);
             {
               const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
               mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
@@ -557,7 +572,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
               __syncwarp();
               ++seq;
             }
-            // ---- W_lo slot: D += Ahi*Wlo ----
             {
               const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
               mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
@@ -570,22 +584,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
                 umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
                 if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
                 umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+                if (b == 1 && !lin_in) umma_commit_pair(bar_base + (BAR_A_FREE + j) * 8);
               }
               __syncwarp();
               ++seq;
             }
           }
-          if (!lin_in) {
-            if (issuer) umma_commit_pair(bar_base + (BAR_A_FREE + j) * 8);   // chunk j may be overwritten (early gather staging)
-            __syncwarp();
-          }
+          if (issuer) umma_commit_pair(bar_base + (BAR_ACC + b) * 8);
+          __syncwarp();
         }
         if (lin_in) f_phase ^= 1; else a_phase ^= 1;
-        if (issuer) {
-          umma_commit_pair(bar_base + BAR_ACC * 8);
-          *reinterpret_cast<volatile long long*>(smem + SM_TSTAMP) = clock64();
-        }
-        __syncwarp();
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
         for (int v = 0; v < NS; ++v) {
@@ -640,8 +648,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       };
       auto stream_fc = [&](int layer) {  // layer 0..9 = fc_0/fc_1 of blocks 0..4, k-chunks in MMA order
         const int base = SLOTS_LIN_IN + layer * SLOTS_FC;
-        for (int jj = 0; jj < 8; ++jj)
-          for (int r = 0; r < 4; ++r) stream_slot(base + chunk_order(jj) * 4 + r);
+        for (int b = 0; b < 2; ++b)
+          for (int jj = 0; jj < 8; ++jj) {
+            stream_slot(base + chunk_order(jj) * 4 + b * 2 + 0);
+            stream_slot(base + chunk_order(jj) * 4 + b * 2 + 1);
+          }
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
         for (int v = 0; v < NS; ++v) {
