@@ -180,20 +180,53 @@ __device__ __forceinline__ void stage_gather_chunk(uint8_t* smem, uint32_t smem_
                                                    int j, int warp, int lane) {
   const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
   const int sub = lane >> 4, l16 = lane & 15;
+  // both row pairs of this warp: all 8 tap loads are issued before the first use (one L2 round trip, not two)
+  float4 t[2][4];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const uint32_t* geo = geo_all + (warp * 4 + it * 2 + sub) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[it][k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + j * 64) + l16);
+  }
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int row = warp * 4 + it * 2 + sub;
     const uint32_t* geo = geo_all + row * 8;
-    float4 t[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + j * 64) + l16);
     const float w0 = __uint_as_float(geo[4]), w1 = __uint_as_float(geo[5]), w2 = __uint_as_float(geo[6]),
                 w3 = __uint_as_float(geo[7]);
     float4 g;
-    g.x = ((t[0].x * w0 + t[1].x * w1) + t[2].x * w2) + t[3].x * w3;
-    g.y = ((t[0].y * w0 + t[1].y * w1) + t[2].y * w2) + t[3].y * w3;
-    g.z = ((t[0].z * w0 + t[1].z * w1) + t[2].z * w2) + t[3].z * w3;
-    g.w = ((t[0].w * w0 + t[1].w * w1) + t[2].w * w2) + t[3].w * w3;
+    g.x = ((t[it][0].x * w0 + t[it][1].x * w1) + t[it][2].x * w2) + t[it][3].x * w3;
+    g.y = ((t[it][0].y * w0 + t[it][1].y * w1) + t[it][2].y * w2) + t[it][3].y * w3;
+    g.z = ((t[it][0].z * w0 + t[it][1].z * w1) + t[it][2].z * w2) + t[it][3].z * w3;
+    g.w = ((t[it][0].w * w0 + t[it][1].w * w1) + t[it][2].w * w2) + t[it][3].w * w3;
+    st_shared_f4(smem_u + a_unit_offset(j, row, l16 >> 1) + ((l16 & 1) ? 8192u : 0u), g);
+  }
+}
+// two chunks at once (the two chunks of an epilogue wave): 16 tap loads in flight per lane
+__device__ __forceinline__ void stage_gather_pair(uint8_t* smem, uint32_t smem_u, const float* __restrict__ proj_i,
+                                                  int j0, int j1, int warp, int lane) {
+  const uint32_t* geo_all = reinterpret_cast<const uint32_t*>(smem + SM_GEO);
+  const int sub = lane >> 4, l16 = lane & 15;
+  float4 t[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t* geo = geo_all + (warp * 4 + (q & 1) * 2 + sub) * 8;
+    const int j = (q >> 1) ? j1 : j0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[q][k] = __ldg(reinterpret_cast<const float4*>(proj_i + geo[k] + j * 64) + l16);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int row = warp * 4 + (q & 1) * 2 + sub;
+    const int j = (q >> 1) ? j1 : j0;
+    const uint32_t* geo = geo_all + row * 8;
+    const float w0 = __uint_as_float(geo[4]), w1 = __uint_as_float(geo[5]), w2 = __uint_as_float(geo[6]),
+                w3 = __uint_as_float(geo[7]);
+    float4 g;
+    g.x = ((t[q][0].x * w0 + t[q][1].x * w1) + t[q][2].x * w2) + t[q][3].x * w3;
+    g.y = ((t[q][0].y * w0 + t[q][1].y * w1) + t[q][2].y * w2) + t[q][3].y * w3;
+    g.z = ((t[q][0].z * w0 + t[q][1].z * w1) + t[q][2].z * w2) + t[q][3].z * w3;
+    g.w = ((t[q][0].w * w0 + t[q][1].w * w1) + t[q][2].w * w2) + t[q][3].w * w3;
     st_shared_f4(smem_u + a_unit_offset(j, row, l16 >> 1) + ((l16 & 1) ? 8192u : 0u), g);
   }
 }
@@ -223,11 +256,12 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
   for (int half = 0; half < 2; ++half) {
     if (MODE == MODE_GATHER && gate && half == 1) {
       // the tail of the running layer releases chunks 4, 6, 5, 7: stage them before its accumulator barrier
-      for (int jj = 4; jj < 8; ++jj) {
-        const int jf = chunk_order(jj);
-        mbar_wait(c.bar_base + (BAR_A_FREE + jf) * 8, free_par, p.status, 140 + jf);
-        stage_gather_chunk(c.smem, c.smem_u, proj_i, jf, warp, c.lane);
-      }
+      mbar_wait(c.bar_base + (BAR_A_FREE + 4) * 8, free_par, p.status, 144);
+      mbar_wait(c.bar_base + (BAR_A_FREE + 6) * 8, free_par, p.status, 146);
+      stage_gather_pair(c.smem, c.smem_u, proj_i, 4, 6, warp, c.lane);
+      mbar_wait(c.bar_base + (BAR_A_FREE + 5) * 8, free_par, p.status, 145);
+      mbar_wait(c.bar_base + (BAR_A_FREE + 7) * 8, free_par, p.status, 147);
+      stage_gather_pair(c.smem, c.smem_u, proj_i, 5, 7, warp, c.lane);
       workers_sync();
     }
     mbar_wait_timed(c.bar_base + (BAR_ACC + half) * 8, acc_phase, p.status, tag + half, *c.t_acc);
@@ -253,8 +287,7 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
             const int j0 = ((i >> 1) & 1), j1 = j0 + 2;
             mbar_wait(c.bar_base + (BAR_A_FREE + j0) * 8, free_par, p.status, 140 + j0);
             mbar_wait(c.bar_base + (BAR_A_FREE + j1) * 8, free_par, p.status, 140 + j1);
-            stage_gather_chunk(c.smem, c.smem_u, proj_i, j0, warp, c.lane);
-            stage_gather_chunk(c.smem, c.smem_u, proj_i, j1, warp, c.lane);
+            stage_gather_pair(c.smem, c.smem_u, proj_i, j0, j1, warp, c.lane);
             workers_sync();
           }
         } else if (produce) {
