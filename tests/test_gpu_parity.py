@@ -118,3 +118,24 @@ def test_no_cpu_fallback():
     net = gpu_util.build_net(case, device="cpu", engine="simt")
     with torch.no_grad(), pytest.raises(RuntimeError):
         net(case["ref"]["field_xyz"], coarse=True, viewdirs=case["ref"]["field_dirs"])
+
+
+@pytest.mark.parametrize("n_fine,n_fine_depth", [(6, 0), (5, 5), (0, 0)])
+def test_sample_count_edge_cases(n_fine, n_fine_depth):
+    """No depth samples / no importance samples / coarse only (nerf.py:284-293 skips the empty sampler)."""
+    import gpu_util
+    case = gu.load_case("tiny")
+    cfg = dict(case["cfg"])
+    cfg.update(n_fine=n_fine, n_fine_depth=n_fine_depth)
+    case = dict(case, cfg=cfg)
+    R = case["rays"].shape[0] * case["rays"].shape[1]
+    case["noise"] = gu.synth.draw_noise(77, R, cfg["n_coarse"], n_fine, n_fine_depth)
+    res = gpu_util.render_case_cuda(case, engine="simt")
+    ref = gu.oracle_render(case)
+    assert (res["coarse"]["rgb"].cpu() - ref["coarse"]["rgb"]).abs().max() < 1e-4
+    if n_fine > 0:
+        flipped = ((res["fine"]["z"].cpu() - ref["fine"]["z"]).abs() > 2e-4).any(dim=-1)
+        assert flipped.float().mean() <= 0.1
+        assert (res["fine"]["rgb"].cpu()[~flipped] - ref["fine"]["rgb"][~flipped]).abs().max() < 1e-4
+    else:
+        assert "fine" not in res
