@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
@@ -112,8 +112,16 @@ class ClockSampler(threading.Thread):
         sm = sorted(int(float(s[0])) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+               "samples": len(sm)}
+        try:    # board power next to the clocks: the kernel runs against the power limit, not the clock limit
+            pw = sorted(float(s[6]) for s in self.samples if len(s) >= 8)
+            if pw:
+                out["power_w"] = pw[len(pw) // 2]
+                out["power_limit_w"] = float(self.samples[0][7])
+        except ValueError:
+            pass
+        return out
 
 
 def model_conf(cfg):
@@ -253,6 +261,14 @@ def run_ours(args):
     rays_per_rank_total = n_rays * args.steps
     kern_tflops = (rays_per_rank_total * fl / 1e12) / (kern_ms / 1e3) if kern_ms > 0 else None
 
+    # fp16 tensor work the tensor engine actually issues: 3 split products over lin_in (K padded to 48) and the
+    # 10 fc layers; the three lin_z GEMMs are folded into the per-scene projected-latent maps
+    d = cfg["d_hidden"]
+    pts = cfg["n_coarse"] + ((cfg["n_coarse"] + cfg["n_fine"]) if cfg["n_fine"] > 0 else 0)
+    exec_fl = 2 * 3 * pts * (cfg["NS"] * (48 * d + 6 * d * d) + 4 * d * d)
+    exec_tflops = (rays_per_rank_total * exec_fl / 1e12) / (kern_ms / 1e3) if kern_ms > 0 else None
+    tensor_engine = net._fused.mlp.get("mlp_coarse", (0, 0, 0, None))[3] is not None
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_run(cfg, sample_rays=args.cpu_rays, reps=1)
@@ -278,6 +294,8 @@ def run_ours(args):
                          "traffic_note": "dram bytes per launch from profiles/r1_final_k_field_tc.txt (same command under ncu); "
                                          "dominated by the write-back / refetch caused by the 256 MB L2 flush between steps",
                          "kernel_ms_per_step": kern_ms / args.steps,
+                         "executed_fp16_mma_tflops": exec_tflops if tensor_engine else None,
+                         "executed_frac_of_peak": (exec_tflops / peak) if (tensor_engine and exec_tflops) else None,
                          "note": "algorithmic fp32-model FLOPs of the reference (SURVEY 8d) / device time of the "
                                  "MLP-contraction kernel(s), CUDA events on the launch stream"},
             "clocks": sampler.summary(),

@@ -567,78 +567,87 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       const uint32_t a_base = smem_u32(smem + SM_A), b_base = smem_u32(smem + SM_B);
       const uint64_t desc0 = make_desc(0);   // address field is added per operand (16-byte units)
       const bool issuer = elect_one();
-      auto run_layer = [&](uint32_t dcol, bool overwrite, int nchunks, int ksteps, bool lin_in) {
-        // feature-block outer: all k-chunks for output features 0..255, then 256..511, so that the epilogue of
-        // block 0 overlaps the MMAs of block 1 and the next layer can start without a bubble (the A chunks are
-        // waited for in the first pass only; the second pass releases them chunk by chunk)
+      // one (feature block b, k-chunk j) step: W_hi slot (Ahi*Whi, Alo*Whi) then W_lo slot (Ahi*Wlo)
+      auto mma_step = [&](uint32_t d, int j, int ksteps, bool zero_acc, bool release_a) {
+        const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
+        const uint64_t a_lo = a_hi + (8192 >> 4);
+        {
+          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+          mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+          mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+          tc_fence_after();
+          const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
+          if (issuer) {
+            umma_f16_2sm(d, a_hi, bd, IDESC, zero_acc ? 0u : 1u);
+            umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
+            umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
+            if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
+            umma_f16_2sm(d, a_lo, bd, IDESC, 1u);
+            umma_f16_2sm(d, a_lo + 2, bd + 2, IDESC, 1u);
+            umma_f16_2sm(d, a_lo + 4, bd + 4, IDESC, 1u);
+            if (ksteps == 4) umma_f16_2sm(d, a_lo + 6, bd + 6, IDESC, 1u);
+            umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+          }
+          __syncwarp();
+          ++seq;
+        }
+        {
+          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+          mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
+          mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
+          tc_fence_after();
+          const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
+          if (issuer) {
+            umma_f16_2sm(d, a_hi, bd, IDESC, 1u);
+            umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
+            umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
+            if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
+            umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
+            if (release_a) umma_commit_pair(bar_base + (BAR_A_FREE + j) * 8);
+          }
+          __syncwarp();
+          ++seq;
+        }
+      };
+      auto run_lin_in = [&]() {   // K = 42 -> 48, one chunk, both feature blocks
 #pragma unroll 1
         for (int b = 0; b < 2; ++b) {
-          const uint32_t d = tmem_base + dcol + b * 128;
-          for (int jj = 0; jj < nchunks; ++jj) {
-            const int j = lin_in ? 0 : chunk_order(jj);
-            if (b == 0) {
-              if (lin_in) {
-                mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
-              } else {
-                mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, jj == 0 ? t_afull : t_alater);
-              }
-            }
-            const uint64_t a_hi = desc0 + ((a_base + j * A_CHUNK_BYTES) >> 4);
-            const uint64_t a_lo = a_hi + (8192 >> 4);
-            {
-              const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-              mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
-              mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
-              tc_fence_after();
-              const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
-              if (issuer) {
-                umma_f16_2sm(d, a_hi, bd, IDESC, (overwrite && jj == 0) ? 0u : 1u);
-                umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
-                umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
-                if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
-                umma_f16_2sm(d, a_lo, bd, IDESC, 1u);
-                umma_f16_2sm(d, a_lo + 2, bd + 2, IDESC, 1u);
-                umma_f16_2sm(d, a_lo + 4, bd + 4, IDESC, 1u);
-                if (ksteps == 4) umma_f16_2sm(d, a_lo + 6, bd + 6, IDESC, 1u);
-                umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
-              }
-              __syncwarp();
-              ++seq;
-            }
-            {
-              const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-              mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 200 + sl, t_bfull);
-              mbar_wait_spin(bar_base + (BAR_B_PEER + sl) * 8, ph, p.status, 210 + sl, t_bpeer);
-              tc_fence_after();
-              const uint64_t bd = desc0 + ((b_base + sl * SLOT_BYTES) >> 4);
-              if (issuer) {
-                umma_f16_2sm(d, a_hi, bd, IDESC, 1u);
-                umma_f16_2sm(d, a_hi + 2, bd + 2, IDESC, 1u);
-                umma_f16_2sm(d, a_hi + 4, bd + 4, IDESC, 1u);
-                if (ksteps == 4) umma_f16_2sm(d, a_hi + 6, bd + 6, IDESC, 1u);
-                umma_commit_pair(bar_base + (BAR_B_EMPTY + sl) * 8);
-                if (b == 1 && !lin_in) umma_commit_pair(bar_base + (BAR_A_FREE + j) * 8);
-              }
-              __syncwarp();
-              ++seq;
-            }
-          }
+          if (b == 0) mbar_wait_spin(bar_base + BAR_F_FULL * 8, f_phase, p.status, 220, t_afull);
+          mma_step(tmem_base + X_COL + b * 128, 0, 3, true, false);
           if (issuer) umma_commit_pair(bar_base + (BAR_ACC + b) * 8);
           __syncwarp();
         }
-        if (lin_in) f_phase ^= 1; else a_phase ^= 1;
+        f_phase ^= 1;
+      };
+      auto run_layer = [&](uint32_t dcol, bool overwrite) {
+        // Feature-block-major with a skew (fc_step_order): the epilogue of block 0 overlaps the tail of block 1 and
+        // the epilogue of block 1 overlaps the head of the next layer, both with about the same cover.  A chunks are
+        // waited for at their first use (block 0) and released after their last (block 1).
+#pragma unroll 1
+        for (int t = 0; t < 16; ++t) {
+          const int code = fc_step_order(t), b = code >> 3, jj = code & 7;
+          const int j = chunk_order(jj);
+          if (b == 0)
+            mbar_wait_spin(bar_base + (BAR_A_FULL + j) * 8, a_phase, p.status, 230 + j, jj == 0 ? t_afull : t_alater);
+          mma_step(tmem_base + dcol + b * 128, j, 4, overwrite && jj == 0, b == 1);
+          if (jj == 7) {
+            if (issuer) umma_commit_pair(bar_base + (BAR_ACC + b) * 8);
+            __syncwarp();
+          }
+        }
+        a_phase ^= 1;
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
         for (int v = 0; v < NS; ++v) {
-          run_layer(X_COL, true, 1, 3, true);                 // lin_in (K = 42 -> 48)
+          run_lin_in();
           for (int blk = 0; blk < 3; ++blk) {
-            run_layer(H_COL, true, 8, 4, false);              // fc_0
-            run_layer(X_COL, false, 8, 4, false);             // fc_1 accumulates onto the residual
+            run_layer(H_COL, true);              // fc_0
+            run_layer(X_COL, false);             // fc_1 accumulates onto the residual
           }
         }
         for (int blk = 3; blk < 5; ++blk) {
-          run_layer(H_COL, true, 8, 4, false);
-          run_layer(X_COL, false, 8, 4, false);
+          run_layer(H_COL, true);
+          run_layer(X_COL, false);
         }
       }
       if (lane == 0) {
@@ -681,11 +690,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       };
       auto stream_fc = [&](int layer) {  // layer 0..9 = fc_0/fc_1 of blocks 0..4, k-chunks in MMA order
         const int base = SLOTS_LIN_IN + layer * SLOTS_FC;
-        for (int b = 0; b < 2; ++b)
-          for (int jj = 0; jj < 8; ++jj) {
-            stream_slot(base + chunk_order(jj) * 4 + b * 2 + 0);
-            stream_slot(base + chunk_order(jj) * 4 + b * 2 + 1);
-          }
+        for (int t = 0; t < 16; ++t) {
+          const int code = fc_step_order(t), b = code >> 3, jj = code & 7;
+          stream_slot(base + chunk_order(jj) * 4 + b * 2 + 0);
+          stream_slot(base + chunk_order(jj) * 4 + b * 2 + 1);
+        }
       };
       for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
         for (int v = 0; v < NS; ++v) {

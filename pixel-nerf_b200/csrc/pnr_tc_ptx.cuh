@@ -172,6 +172,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
 }
 // k-chunks of a layer are produced by the workers in 4 waves (0,2 | 1,3 | 4,6 | 5,7); the MMA consumes in that order
 __device__ __forceinline__ int chunk_order(int jj) { return (jj & 4) | ((jj & 1) << 1) | ((jj >> 1) & 1); }
+// Order of the 16 (feature block b, chunk position jj) steps of a 512x512 layer, as b*8+jj.  Block 0 over chunk
+// positions 0-3, PNR_TC_SKEW early block-1 steps, block 0 over 4-7, the rest of block 1.  Skew 0 is plain block-major.
+#ifndef PNR_TC_SKEW
+#define PNR_TC_SKEW 0
+#endif
+__device__ __forceinline__ int fc_step_order(int t) {
+  if (t < 4) return t;                                   // b0 jj 0..3
+  if (t < 4 + PNR_TC_SKEW) return 8 + (t - 4);           // b1 jj 0..SKEW-1
+  if (t < 8 + PNR_TC_SKEW) return t - PNR_TC_SKEW;       // b0 jj 4..7
+  return t;                                              // b1 jj SKEW..7
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
