@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 1
+#define PNR_ABI_VERSION 2
 #define PNR_MAX_BLOCKS 8
 
 enum {
@@ -131,6 +131,19 @@ int pnr_pack_latent(const float* latent_nchw, float* latent_nhwc, int32_t V, int
 /* NeRFRenderer.sample_coarse (nerf.py:98-118, lindisp=False).  rays [R][8] -> z [R][Kc]. */
 int pnr_sample_coarse(const float* rays, const float* lin_steps, const float* u_coarse, float* z,
                       int64_t R, int32_t Kc, void* stream);
+
+/* util.gen_rays with unproj_map (src/util/util.py:238-276, :113-143; ndc=False): rays of pixels
+ * [first, first+count) of the flattened (NV, H, W) grid of NV camera-to-world poses [NV][4][4] ->
+ * rays [count][8] = [origin, unit dir, z_near, z_far].  The caller's split loop
+ * (eval/gen_video.py:209-212) can so generate each ray batch in place instead of holding (NV,H,W,8). */
+int pnr_gen_rays(const float* poses_c2w, int64_t NV, int32_t W, int32_t H, float fx, float fy, float cx,
+                 float cy, float z_near, float z_far, int64_t first, int64_t count, float* rays,
+                 void* stream);
+
+/* Frame assembly of eval/gen_video.py:213-222 + :236: out[i] = (uint8)(rgb[i] * 255), truncating
+ * (numpy astype); n = number of float values (rays * 3).  Values outside [0, 256/255) wrap like the
+ * x86 cast (low 8 bits of the truncated int32). */
+int pnr_frames_u8(const float* rgb, int64_t n, uint8_t* out, void* stream);
 
 /* Compositing tail of NeRFRenderer.composite (nerf.py:178-182, 222-249) given the field
  * values field [R][K][4] = (sigmoid rgb, relu sigma).  weights may be NULL. */

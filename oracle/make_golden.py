@@ -175,6 +175,20 @@ def util_fixture(check):
     print("util_rays: written")
 
 
+def frames_fixture():
+    """(frames * 255).astype(uint8) exactly as eval/gen_video.py:236 writes it, on colours that include the
+    interesting boundaries (0, k/255 +- 1 ulp, 1.0, just above 1.0)."""
+    g = torch.Generator().manual_seed(77)
+    rgb = torch.rand(2, 5, 7, 3, generator=g)
+    edge = torch.tensor([0.0, 1.0, 1.0000001, 0.5, 128 / 255, 127.999 / 255, 254.99999 / 255, 1e-8, 0.99999994,
+                         3 / 255, 1 / 255, 0.003921569])
+    rgb.view(-1)[: edge.numel()] = edge
+    frames = rgb.view(-1, 5, 7, 3)
+    u8 = (frames.cpu().numpy() * 255).astype(np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "frames_u8.npz"), rgb=rgb.numpy(), u8=u8)
+    print("frames_u8: written")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -188,3 +202,5 @@ if __name__ == "__main__":
         run_case(name, cs, a.check)
     if not a.only:
         util_fixture(a.check)
+    if not a.only or a.only == "frames_u8":
+        frames_fixture()

@@ -262,3 +262,33 @@ def render(rays, noise, state, latent, w_coarse, w_fine, NS, n_coarse, n_fine, n
                                   eval_batch_size)
         res["fine"] = dict(weights=wts, rgb=rgbf, depth=df, z=z_comb)
     return res
+
+
+# ----------------------------------------------------------------------------------------
+# caller-side rows: ray generation and frame assembly
+# ----------------------------------------------------------------------------------------
+
+
+def gen_rays(poses, width, height, fx, fy, cx, cy, z_near, z_far):
+    """util.gen_rays + unproj_map with ndc=False (src/util/util.py:238-276, :113-143).
+    poses (NV,4,4) camera-to-world -> (NV,H,W,8) [origin, unit direction, near, far]."""
+    ys = (torch.arange(height, dtype=torch.float32) - float(cy)) / float(fy)     # util.py:134-139
+    xs = (torch.arange(width, dtype=torch.float32) - float(cx)) / float(fx)
+    X = xs[None, :].expand(height, width)
+    Y = ys[:, None].expand(height, width)
+    cam = torch.stack((X, -Y, -torch.ones_like(X)), dim=-1)                       # :141
+    cam = cam / torch.norm(cam, dim=-1).unsqueeze(-1)                             # :142
+    nv = poses.shape[0]
+    dirs = torch.matmul(poses[:, None, None, :3, :3], cam[None].expand(nv, -1, -1, -1).unsqueeze(-1))[..., 0]
+    origins = poses[:, None, None, :3, 3].expand(-1, height, width, -1)          # util.py:251-254
+    near = torch.full((nv, height, width, 1), float(z_near))
+    far = torch.full((nv, height, width, 1), float(z_far))
+    return torch.cat((origins, dirs, near, far), dim=-1)                          # :274-276
+
+
+def frames_u8(rgb):
+    """Frame assembly of eval/gen_video.py:213-222 and :236: `(frames.cpu().numpy() * 255).astype(np.uint8)`,
+    i.e. an fp32 multiply and a truncating cast.  rgb: float32 tensor -> uint8 numpy array of the same shape.
+    Defined for values in [0, 256/255) only (the cast is implementation-defined outside)."""
+    import numpy as np
+    return (rgb.detach().cpu().numpy().astype(np.float32) * 255).astype(np.uint8)

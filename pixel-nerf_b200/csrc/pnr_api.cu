@@ -151,6 +151,26 @@ int pnr_sample_coarse(const float* rays, const float* lin_steps, const float* u_
   return launch_sample_coarse(rays, lin_steps, u_coarse, z, R, Kc, (cudaStream_t)stream);
 }
 
+int pnr_gen_rays(const float* poses_c2w, int64_t NV, int32_t W, int32_t H, float fx, float fy, float cx, float cy,
+                 float z_near, float z_far, int64_t first, int64_t count, float* rays, void* stream) {
+  PNR_CHECK_ARG(NV >= 0 && W >= 1 && H >= 1, "bad sizes");
+  PNR_CHECK_ARG(first >= 0 && count >= 0 && first + count <= NV * (int64_t)W * H, "ray range outside the pixel grid");
+  if (count == 0) return PNR_OK;
+  PNR_CHECK_ARG(poses_c2w && rays, "NULL pointer");
+  PNR_CHECK_ARG(fx != 0.f && fy != 0.f, "zero focal length");
+  PNR_CHECK_ARG((reinterpret_cast<uintptr_t>(rays) & 15) == 0, "rays must be 16-byte aligned");
+  return launch_gen_rays(poses_c2w, W, H, fx, fy, cx, cy, z_near, z_far, first, count, rays, (cudaStream_t)stream);
+}
+
+int pnr_frames_u8(const float* rgb, int64_t n, uint8_t* out, void* stream) {
+  PNR_CHECK_ARG(n >= 0, "bad size");
+  if (n == 0) return PNR_OK;
+  PNR_CHECK_ARG(rgb && out, "NULL pointer");
+  PNR_CHECK_ARG((reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                "rgb must be 16-byte and out 4-byte aligned");
+  return launch_frames_u8(rgb, n, out, (cudaStream_t)stream);
+}
+
 int pnr_composite(const float* rays, const float* z, const float* field, int32_t white_bkgd, float* weights,
                   float* rgb, float* depth, int64_t R, int32_t K, void* stream) {
   PNR_CHECK_ARG(R >= 0 && K >= 1, "bad sizes");

@@ -88,6 +88,11 @@ int launch_sample_fine(const float* rays, const float* zc, const float* wc, cons
 int launch_build_rows(const PnrScene& sc, const PointSource& src, int64_t g0, int64_t n_pts, float* feat,
                       float* lat, cudaStream_t s);
 
+// rays of pixels [first, first+count) of the flattened (NV,H,W) grid; rgb floats -> uint8 frame bytes
+int launch_gen_rays(const float* poses, int W, int H, float fx, float fy, float cx, float cy, float z_near,
+                    float z_far, int64_t first, int64_t count, float* rays, cudaStream_t s);
+int launch_frames_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t s);
+
 // ---- SIMT engine (pnr_field_simt.cu) ---------------------------------------------------
 size_t simt_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);
 int simt_field_eval(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src, int64_t total_points,

@@ -253,4 +253,80 @@ int launch_build_rows(const PnrScene& sc, const PointSource& src, int64_t g0, in
   return PNR_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// ray generation (src/util/util.py:238-276 gen_rays, :113-143 unproj_map).  Ray i of the flattened
+// (NV, H, W) pixel grid, i in [first, first+count): [origin(3), unit dir(3), near, far].  One thread
+// computes one ray; a warp then writes its 32 rays (1 KB) with two fully coalesced float4 stores.
+// ----------------------------------------------------------------------------------------
+__global__ void k_gen_rays(const float* __restrict__ poses, int W, int H, float fx, float fy, float cx, float cy,
+                           float z_near, float z_far, int64_t first, int64_t count, float* __restrict__ rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t warp_base = t - lane;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (t < count) {
+    const int64_t i = first + t, hw = (int64_t)W * H;
+    const int64_t v = i / hw;
+    const int rem = (int)(i - v * hw);
+    const int y = rem / W, x = rem - y * W;
+    const float* P = poses + v * 16;                 // camera-to-world, row-major 4x4
+    const float X = ((float)x - cx) / fx;            // unproj_map: (arange - c) / f
+    const float Y = ((float)y - cy) / fy;
+    float dx = X, dy = -Y, dz = -1.0f;
+    const float n = sqrtf((dx * dx + dy * dy) + dz * dz);
+    dx = dx / n; dy = dy / n; dz = dz / n;
+    o[0] = P[3]; o[1] = P[7]; o[2] = P[11];
+    o[3] = (P[0] * dx + P[1] * dy) + P[2] * dz;
+    o[4] = (P[4] * dx + P[5] * dy) + P[6] * dz;
+    o[5] = (P[8] * dx + P[9] * dy) + P[10] * dz;
+    o[6] = z_near; o[7] = z_far;
+  }
+  float4* dst = reinterpret_cast<float4*>(rays) + warp_base * 2;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int q = s * 32 + lane, src = q >> 1, half = q & 1;   // float4 q of the warp's 64
+    float4 lo, hi;
+    lo.x = __shfl_sync(0xffffffffu, o[0], src); lo.y = __shfl_sync(0xffffffffu, o[1], src);
+    lo.z = __shfl_sync(0xffffffffu, o[2], src); lo.w = __shfl_sync(0xffffffffu, o[3], src);
+    hi.x = __shfl_sync(0xffffffffu, o[4], src); hi.y = __shfl_sync(0xffffffffu, o[5], src);
+    hi.z = __shfl_sync(0xffffffffu, o[6], src); hi.w = __shfl_sync(0xffffffffu, o[7], src);
+    if (warp_base + src < count) dst[q] = half ? hi : lo;
+  }
+}
+
+int launch_gen_rays(const float* poses, int W, int H, float fx, float fy, float cx, float cy, float z_near,
+                    float z_far, int64_t first, int64_t count, float* rays, cudaStream_t s) {
+  if (count == 0) return PNR_OK;
+  k_gen_rays<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(poses, W, H, fx, fy, cx, cy, z_near, z_far, first,
+                                                              count, rays);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// frame assembly (eval/gen_video.py:213-222, 236): (rgb * 255).astype(uint8), i.e. one fp32 multiply and a
+// truncating cast; four values per thread (coalesced 16 B loads, 4 B stores).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int to_u8(float x) { return (unsigned int)__float2int_rz(x * 255.0f) & 255u; }
+
+__global__ void k_frames_u8(const float* __restrict__ rgb, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = q * 4;
+  if (i + 3 < n) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(rgb) + q);
+    const unsigned int w = to_u8(v.x) | (to_u8(v.y) << 8) | (to_u8(v.z) << 16) | (to_u8(v.w) << 24);
+    reinterpret_cast<unsigned int*>(out)[q] = w;
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = (uint8_t)to_u8(rgb[k]);
+  }
+}
+
+int launch_frames_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t s) {
+  if (n == 0) return PNR_OK;
+  const int64_t quads = (n + 3) / 4;
+  k_frames_u8<<<(unsigned)((quads + 255) / 256), 256, 0, s>>>(rgb, n, out);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
 }  // namespace pnr

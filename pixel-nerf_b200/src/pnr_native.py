@@ -75,6 +75,8 @@ def lib():
     L.pnr_pack_latent.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.pnr_sample_coarse.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     L.pnr_composite.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, i32, vp]
+    L.pnr_gen_rays.argtypes = [vp, i64, i32, i32, f32, f32, f32, f32, f32, f32, i64, i64, vp, vp]
+    L.pnr_frames_u8.argtypes = [vp, i64, vp, vp]
     L.pnr_sample_fine.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, vp, i64, i32, i32, i32, vp]
     L.pnr_field_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), i64, i32]
     L.pnr_field_workspace_bytes.restype = sz
@@ -95,9 +97,10 @@ def lib():
     L.pnr_profile_end.argtypes = [P(C.c_double), P(C.c_int64)]
     L.pnr_profile_end.restype = C.c_int
     for name in ("pnr_pack_latent", "pnr_sample_coarse", "pnr_composite", "pnr_sample_fine",
-                 "pnr_field_eval", "pnr_render", "pnr_pack_mlp", "pnr_project_latent"):
+                 "pnr_field_eval", "pnr_render", "pnr_pack_mlp", "pnr_project_latent", "pnr_gen_rays",
+                 "pnr_frames_u8"):
         getattr(L, name).restype = C.c_int
-    if L.pnr_abi_version() != 1:
+    if L.pnr_abi_version() != 2:
         raise RuntimeError("libpnr_sm100.so ABI version mismatch")
     _lib = L
     return L
@@ -121,6 +124,36 @@ def dptr(t, name="tensor"):
 
 def stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def gen_rays(poses, width, height, fx, fy, cx, cy, z_near, z_far, first=0, count=None, out=None):
+    """pnr_gen_rays: rays [count][8] of pixels [first, first+count) of the (NV,H,W) grid of `poses` (NV,4,4) c2w."""
+    nv = poses.shape[0]
+    total = nv * width * height
+    if count is None:
+        count = total - first
+    poses = poses.to(torch.float32).contiguous()
+    if out is None:
+        out = torch.empty(count, 8, device=poses.device, dtype=torch.float32)
+    elif out.shape != (count, 8):
+        raise RuntimeError(f"gen_rays: out has shape {tuple(out.shape)}, expected {(count, 8)}")
+    with torch.cuda.device(poses.device):
+        check(lib().pnr_gen_rays(dptr(poses, "poses"), nv, int(width), int(height), float(fx), float(fy), float(cx),
+                                 float(cy), float(z_near), float(z_far), int(first), int(count), dptr(out, "rays"),
+                                 stream_ptr(poses.device)))
+    return out
+
+
+def frames_u8(rgb, out=None):
+    """pnr_frames_u8: (rgb * 255).astype(uint8) of a float32 CUDA tensor, same shape."""
+    rgb = rgb.contiguous()
+    if out is None:
+        out = torch.empty(rgb.shape, device=rgb.device, dtype=torch.uint8)
+    elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == rgb.numel()):
+        raise RuntimeError("frames_u8: out must be a contiguous uint8 CUDA tensor with as many elements as rgb")
+    with torch.cuda.device(rgb.device):
+        check(lib().pnr_frames_u8(dptr(rgb, "rgb"), rgb.numel(), C.c_void_p(out.data_ptr()), stream_ptr(rgb.device)))
+    return out
 
 
 def profile_begin():

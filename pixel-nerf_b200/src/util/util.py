@@ -35,8 +35,8 @@ def batched_index_select_nd(t, inds):
     return t.gather(1, idx)
 
 
-def unproj_map(width, height, f, c=None, device="cpu"):
-    """(H, W, 3) unit camera-space ray directions, -z forward, +y up (util.py:113-143)."""
+def _intrinsics(width, height, f, c):
+    """(fx, fy, cx, cy) as python floats: scalar or 2-vector focal, optional centre (util.py:124-133)."""
     if c is None:
         cx, cy = width * 0.5, height * 0.5
     else:
@@ -44,6 +44,12 @@ def unproj_map(width, height, f, c=None, device="cpu"):
         cx, cy = float(cc[0]), float(cc[1])
     ff = torch.as_tensor(f, dtype=torch.float32).reshape(-1)
     fx, fy = (float(ff[0]), float(ff[0])) if ff.numel() == 1 else (float(ff[0]), float(ff[1]))
+    return fx, fy, cx, cy
+
+
+def unproj_map(width, height, f, c=None, device="cpu"):
+    """(H, W, 3) unit camera-space ray directions, -z forward, +y up (util.py:113-143)."""
+    fx, fy, cx, cy = _intrinsics(width, height, f, c)
     ys = (torch.arange(height, dtype=torch.float32) - cy).to(device) / fy
     xs = (torch.arange(width, dtype=torch.float32) - cx).to(device) / fx
     Y = ys[:, None].expand(height, width)
@@ -57,6 +63,10 @@ def gen_rays(poses, width, height, focal, z_near, z_far, c=None, ndc=False):
     if ndc:
         raise NotImplementedError("NDC rays are not used by any shipped config")
     nv, dev = poses.shape[0], poses.device
+    if dev.type == "cuda":     # poses already on the GPU: the pnr_gen_rays kernel (no CPU detour)
+        import pnr_native
+        fx, fy, cx, cy = _intrinsics(width, height, torch.as_tensor(focal).squeeze(), c)
+        return pnr_native.gen_rays(poses, width, height, fx, fy, cx, cy, z_near, z_far).view(nv, height, width, 8)
     cam = unproj_map(width, height, torch.as_tensor(focal).squeeze(), c=c, device=dev)
     dirs = torch.matmul(poses[:, None, None, :3, :3], cam[None].expand(nv, -1, -1, -1).unsqueeze(-1))[..., 0]
     origins = poses[:, None, None, :3, 3].expand(-1, height, width, -1)

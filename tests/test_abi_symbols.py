@@ -15,7 +15,8 @@ def declared_functions():
 def test_header_declares_the_documented_surface():
     names = declared_functions()
     for must in ("pnr_render", "pnr_field_eval", "pnr_sample_coarse", "pnr_composite", "pnr_sample_fine",
-                 "pnr_pack_latent", "pnr_pack_mlp", "pnr_project_latent", "pnr_last_error", "pnr_abi_version"):
+                 "pnr_pack_latent", "pnr_pack_mlp", "pnr_project_latent", "pnr_last_error", "pnr_abi_version",
+                 "pnr_gen_rays", "pnr_frames_u8"):
         assert must in names
 
 
@@ -28,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} declared in pnr.h but not exported"
     lib.pnr_abi_version.restype = ctypes.c_int
-    assert lib.pnr_abi_version() == 1
+    assert lib.pnr_abi_version() == 2
 
 
 def test_python_binding_matches_header_struct_sizes():

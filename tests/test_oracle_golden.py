@@ -67,3 +67,17 @@ def test_util_rays_fixture():
     rays_c = gu.synth.gen_rays(poses[:1], 12, 9, torch.tensor([13.5, 14.0]), 0.1, 5.0,
                                c=torch.tensor([6.5, 4.0]))
     assert np.array_equal(rays_c.numpy(), z["rays_c"])
+
+
+def test_oracle_gen_rays_is_the_reference():
+    """oracle.gen_rays against rays produced by the reference's util.gen_rays (make_golden.util_fixture)."""
+    z = np.load(gu.GOLD + "/util_rays.npz")
+    poses = torch.from_numpy(z["poses"])
+    assert np.array_equal(gu.oracle.gen_rays(poses, 12, 9, 13.5, 13.5, 6.0, 4.5, 0.8, 1.8).numpy(), z["rays"])
+    assert np.array_equal(gu.oracle.gen_rays(poses[:1], 12, 9, 13.5, 14.0, 6.5, 4.0, 0.1, 5.0).numpy(), z["rays_c"])
+
+
+def test_oracle_frames_u8_fixture():
+    z = np.load(gu.GOLD + "/frames_u8.npz")
+    assert np.array_equal(gu.oracle.frames_u8(torch.from_numpy(z["rgb"])), z["u8"])
+    assert z["u8"].reshape(-1)[:4].tolist() == [0, 255, 255, 127]
