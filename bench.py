@@ -245,7 +245,7 @@ def run_ours(args):
     ms_total = timed(step_resident, args.steps)
     kern_ms, kern_launches = pn.profile_end()
     if os.environ.get("PNR_TC_COUNTERS"):
-        names = ["mma_total", "mma_wait_a_first_chunk", "mma_wait_b", "mma_wait_bpeer", "hid_commit_to_pass", "hid_pass_to_publish", "mma_wait_a_later_chunks", "stream_wait_empty"]
+        names = ["mma_total", "mma_wait_a_first_chunk", "mma_wait_b", "mma_wait_bpeer", "unused4", "unused5", "mma_wait_a_later_chunks", "stream_wait_empty"]
         print("tc_counters", dict(zip(names, pn.tc_counters())), file=sys.stderr)
     launches = pn.launch_count() - launches0
     for _ in range(2):

@@ -87,7 +87,6 @@ constexpr int BAR_F_FULL = BAR_A_FREE + 8;
 constexpr int BAR_ACC = BAR_F_FULL + 1;             // [2] accumulator block 0 / block 1 ready
 constexpr int BAR_COUNT = BAR_ACC + 2;
 constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
-constexpr int SM_TSTAMP = SM_TMEM_PTR + 8;   // debug: clock64 of the last accumulator commit (leader CTA)
 
 
 struct Params {
@@ -101,7 +100,6 @@ struct Params {
   int64_t total_points;
   int64_t n_tiles;
   int* status;
-  int spin_acc;    // experiment (PNR_TC2_SPIN_ACC=1): workers spin on the accumulator barrier instead of parking
 };
 
 using namespace tcptx;
@@ -117,7 +115,6 @@ struct WorkerCtx {
   int lane, s, m, n_hi;
   float w_scale, w_inv;
   long long* t_acc;     // cycles spent waiting for the accumulator barrier
-  long long* dbg;       // [0] commit -> worker passes the barrier, [1] barrier -> first wave published (MODE_HIDDEN)
 };
 
 // A worker thread owns row m and 8 "steps" of 8 features per layer:
@@ -432,8 +429,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.w_scale = w_scale;
     c.w_inv = w_inv;
     long long t_acc = 0, t_geo = 0;
-    long long dbg[2] = {0, 0};
-    c.dbg = dbg;
     c.t_acc = &t_acc;
     const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
@@ -546,14 +541,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         }
       }
       workers_sync();  // out_part is reused by the next tile
-    }
-    if (threadIdx.x == 0) {
-      unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p.status + 2);
-      if (rank == 0) {
-        atomicAdd(cnt + 4, (unsigned long long)dbg[0]);
-        atomicAdd(cnt + 5, (unsigned long long)dbg[1]);
-      }
-
     }
   } else if (warp == WARP_MMA) {
     if (rank == 0) {
@@ -836,10 +823,6 @@ int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, cons
   p.out = out;
   p.total_points = total_points;
   p.n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
-  {
-    const char* e = getenv("PNR_TC2_SPIN_ACC");
-    p.spin_acc = (e && e[0] == '1') ? 1 : 0;
-  }
   int rc = tc::get_status_buffer(&p.status);
   if (rc) return rc;
   const int pairs = tc_pairs(p.n_tiles);
@@ -954,8 +937,8 @@ int pnr_tc_status(int* out) {
 
 // Debug: cycle breakdown accumulated over all launches since the last call (summed over the leader CTAs):
 // [0] MMA warp total, [1] its waits for the FIRST A chunk of a layer (layer-boundary bubble), [2] for its own weight
-// slot, [3] for the peer's slot, [4] hidden-layer epilogues: accumulator commit -> workers past the barrier,
-// [5] barrier -> first wave of A chunks published, [6] MMA waits for later A chunks, [7] streamer waits for a free slot.
+// slot, [3] for the peer's slot, [4], [5] unused (0),
+// [6] MMA waits for later A chunks, [7] streamer waits for a free slot.
 // (M-split variant; the N-split variant fills [0] total, [1] chunk waits, [2] weight waits, [4..6] worker totals.)
 int pnr_tc_counters(unsigned long long* out8) {
   int* buf = nullptr;
