@@ -47,6 +47,11 @@ CASES = {
     "tiny_sb2": dict(SB=2, NS=2, W=16, H=12, Hl=6, Wl=8, focal=[15.0, 19.0], c=None, z_near=0.8,
                      z_far=1.8, d_hidden=32, n_coarse=8, n_fine=6, n_fine_depth=2, B=10,
                      white_bkgd=False, eval_batch_size=37, store_weights=True, fine_mlp=False),
+    # same shape as tiny_sb2 (whose random MLP happens to give sigma = 0 everywhere: the all-transparent edge case)
+    # but with a visible object, so that per-object indexing of rays / latents / focal shows up in rgb and weights
+    "sb2_d": dict(SB=2, NS=2, W=16, H=12, Hl=6, Wl=8, focal=[15.0, 19.0], c=None, z_near=0.8,
+                      z_far=1.8, d_hidden=32, n_coarse=8, n_fine=6, n_fine_depth=2, B=12,
+                      white_bkgd=False, eval_batch_size=37, store_weights=True, fine_mlp=True),
     "ns1_coarse_only": dict(SB=1, NS=1, W=16, H=16, Hl=8, Wl=8, focal=16.4, c=None, z_near=0.8,
                             z_far=1.8, d_hidden=128, n_coarse=16, n_fine=0, n_fine_depth=0, B=32,
                             white_bkgd=True, eval_batch_size=50000, store_weights=False,
@@ -175,6 +180,51 @@ def util_fixture(check):
     print("util_rays: written")
 
 
+def grad_fixture(name, check):
+    """Gradients of the reference's own training loss (train/train.py:199-215: render with want_weights, MSE coarse
+    + MSE fine, loss.backward()) w.r.t. every MLP parameter and the latent, with the reference run in grad mode."""
+    cs = CASES[name]
+    inp = case_inputs(name, cs)
+    net, renderer = ref_harness.build_reference(
+        cs["d_hidden"], inp["wc"], inp["wf"], cs["n_coarse"], cs["n_fine"], cs["n_fine_depth"],
+        white_bkgd=cs["white_bkgd"], eval_batch_size=cs["eval_batch_size"])
+    latent = inp["latent"].clone().requires_grad_(True)
+    ref_harness.set_scene(net, latent, inp["src_poses"], inp["focal"], inp["c"], cs["W"], cs["H"])
+    g = torch.Generator().manual_seed(inp["seed"] + 6)
+    gt = torch.rand(cs["SB"], cs["B"], 3, generator=g)
+    torch.manual_seed(inp["seed"] + 4)
+    out = renderer(net, inp["rays"], want_weights=True)
+    crit = torch.nn.MSELoss()                       # loss.get_rgb_loss(conf["loss.rgb"], ...) with use_l1 = False
+    loss = crit(out.coarse.rgb, gt)
+    if cs["n_fine"] > 0:
+        loss = loss * 1.0 + crit(out.fine.rgb, gt) * 1.0
+    loss.backward()
+    rec = dict(loss=np.array(loss.item()), rgb_gt=gt.numpy(), g_latent=latent.grad.numpy())
+    for k, p in net.mlp_coarse.named_parameters():
+        rec["gc/" + k] = p.grad.numpy()
+    if net.mlp_fine is not None:
+        for k, p in net.mlp_fine.named_parameters():
+            rec["gf/" + k] = p.grad.numpy()
+    path = os.path.join(GOLD, "grad_" + name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"grad_{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), loss {loss.item():.6f}")
+    if check:
+        state = oracle.encode_state(inp["src_poses"].reshape(-1, 4, 4), inp["focal"], inp["c"], cs["W"], cs["H"])
+        lat = inp["latent"].clone().requires_grad_(True)
+        wc = {k: v.clone().requires_grad_(True) for k, v in inp["wc"].items()}
+        wf = None if inp["wf"] is None else {k: v.clone().requires_grad_(True) for k, v in inp["wf"].items()}
+        lo = oracle.train_loss(inp["rays"], gt, inp["noise"], state, lat, wc, wf, cs["NS"], cs["n_coarse"],
+                               cs["n_fine"], cs["n_fine_depth"], white_bkgd=cs["white_bkgd"],
+                               eval_batch_size=cs["eval_batch_size"])
+        lo.backward()
+        worst = 0.0
+        for k, v in wc.items():
+            ref = torch.from_numpy(rec["gc/" + k])
+            worst = max(worst, ((v.grad - ref).abs().max() / (ref.abs().max() + 1e-12)).item())
+        print(f"   check: loss {abs(lo.item() - loss.item()):.2e}, coarse-grad worst rel {worst:.2e}, latent "
+              f"{((lat.grad - latent.grad).abs().max() / latent.grad.abs().max()).item():.2e}")
+
+
 def frames_fixture():
     """(frames * 255).astype(uint8) exactly as eval/gen_video.py:236 writes it, on colours that include the
     interesting boundaries (0, k/255 +- 1 ulp, 1.0, just above 1.0)."""
@@ -204,3 +254,6 @@ if __name__ == "__main__":
         util_fixture(a.check)
     if not a.only or a.only == "frames_u8":
         frames_fixture()
+    if not a.only or a.only == "grad":
+        grad_fixture("tiny", a.check)
+        grad_fixture("sb2_d", a.check)

@@ -253,7 +253,9 @@ def render(rays, noise, state, latent, w_coarse, w_fine, NS, n_coarse, n_fine, n
     if n_fine > 0:
         samps = [z_coarse]
         if n_fine - n_fine_depth > 0:
-            samps.append(sample_fine(rays, wc, noise["u_fine"], noise["u_fine_jit"], n_coarse))
+            # the coarse weights are detached (nerf.py:286); the coarse depth below is NOT (nerf.py:289-291), so in
+            # grad mode the fine loss also reaches the coarse MLP through the depth-centred samples
+            samps.append(sample_fine(rays, wc.detach(), noise["u_fine"], noise["u_fine_jit"], n_coarse))
         if n_fine_depth > 0:
             samps.append(sample_fine_depth(rays, dc, noise["n_depth"], depth_std))
         z_comb, _ = torch.sort(torch.cat(samps, dim=-1), dim=-1)
@@ -284,6 +286,22 @@ def gen_rays(poses, width, height, fx, fy, cx, cy, z_near, z_far):
     near = torch.full((nv, height, width, 1), float(z_near))
     far = torch.full((nv, height, width, 1), float(z_far))
     return torch.cat((origins, dirs, near, far), dim=-1)                          # :274-276
+
+
+def train_loss(rays, rgb_gt, noise, state, latent, w_coarse, w_fine, NS, n_coarse, n_fine, n_fine_depth,
+               depth_std=0.01, white_bkgd=True, eval_batch_size=50000, lambda_coarse=1.0, lambda_fine=1.0):
+    """The differentiable loss of a training step, train/train.py:199-212 with the shipped conf
+    (conf/default.conf:60-78: MSE rgb losses, lambda_coarse = lambda_fine = 1):
+    `render_par(all_rays, want_weights=True)` then MSE(coarse.rgb, gt) * lc + MSE(fine.rgb, gt) * lf.
+    Every function above is plain differentiable torch, so `train_loss(...).backward()` is the oracle for the
+    backward pass: gradients w.r.t. the MLP weight dicts and `latent`."""
+    res = render(rays, noise, state, latent, w_coarse, w_fine, NS, n_coarse, n_fine, n_fine_depth,
+                 depth_std=depth_std, white_bkgd=white_bkgd, eval_batch_size=eval_batch_size)
+    gt = rgb_gt.reshape(-1, 3)
+    loss = F.mse_loss(res["coarse"]["rgb"], gt)
+    if "fine" in res:
+        loss = loss * lambda_coarse + F.mse_loss(res["fine"]["rgb"], gt) * lambda_fine
+    return loss
 
 
 def frames_u8(rgb):

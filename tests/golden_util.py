@@ -22,6 +22,10 @@ synth = load_by_path("pnr_synth", os.path.join(ROOT, "pixel-nerf_b200", "synth.p
 oracle = load_by_path("pnr_oracle", os.path.join(ROOT, "oracle", "pnr_oracle.py"))
 
 CASE_NAMES = ["tiny", "tiny_sb2", "ns1_coarse_only", "c2_small", "c3_small", "c4_small"]
+# cases that so far pin the ORACLE only (CPU): sb2_d = tiny_sb2's shapes with a visible object in both passes
+# (tiny_sb2's random MLP gives sigma = 0 everywhere: the all-transparent edge case)
+ORACLE_CASE_NAMES = CASE_NAMES + ["sb2_d"]
+GRAD_CASE_NAMES = ["tiny", "sb2_d"]
 
 
 def load_case(name):
@@ -58,3 +62,12 @@ def oracle_render(case):
     return oracle.render(case["rays"], case["noise"], oracle_state(case), case["latent"], case["wc"],
                          case["wf"], cfg["NS"], cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"],
                          white_bkgd=bool(cfg["white_bkgd"]), eval_batch_size=cfg["eval_batch_size"])
+
+
+def load_grad_case(name):
+    """Reference-generated gradients of the training loss (oracle/make_golden.py::grad_fixture)."""
+    z = np.load(os.path.join(GOLD, "grad_" + name + ".npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    return dict(loss=float(z["loss"]), rgb_gt=t("rgb_gt"), g_latent=t("g_latent"),
+                gc={k[3:]: t(k) for k in z.files if k.startswith("gc/")},
+                gf={k[3:]: t(k) for k in z.files if k.startswith("gf/")})

@@ -112,6 +112,36 @@ def test_autograd_path_matches_reference_goldens():
     assert net.mlp_fine.lin_in.weight.grad is not None
 
 
+@pytest.mark.parametrize("name", gu.GRAD_CASE_NAMES)
+def test_training_step_gradients_match_reference(name):
+    """train/train.py:199-215 through this package's classes in grad mode (`render_par(rays, want_weights=True)`,
+    MSE coarse + MSE fine, backward): the gradients of every MLP parameter and of the latent equal the ones the
+    reference computed for the same inputs and seed (tests/golden/grad_*.npz)."""
+    case, g = gu.load_case(name), gu.load_grad_case(name)
+    net = gpu_util.build_net(case, device="cpu", engine="simt").train()
+    net.encoder.latent = case["latent"].clone().requires_grad_(True)
+    renderer = gpu_util.build_renderer(case).train()
+    render_par = renderer.bind_parallel(net, None).train()
+    torch.manual_seed(case["seed"] + 4)
+    out = render_par(case["rays"], want_weights=True)
+    crit = torch.nn.MSELoss()
+    loss = crit(out["coarse"]["rgb"], g["rgb_gt"])
+    if case["cfg"]["n_fine"] > 0:
+        loss = loss * 1.0 + crit(out["fine"]["rgb"], g["rgb_gt"]) * 1.0
+    assert abs(loss.item() - g["loss"]) < 1e-6
+    loss.backward()
+
+    def close(a, ref):
+        return (a - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-9
+
+    assert close(net.encoder.latent.grad, g["g_latent"])
+    for k, p in net.mlp_coarse.named_parameters():
+        assert close(p.grad, g["gc"][k]), ("coarse", k)
+    if net.mlp_fine is not None:
+        for k, p in net.mlp_fine.named_parameters():
+            assert close(p.grad, g["gf"][k]), ("fine", k)
+
+
 def test_dotmap_compat():
     from render.dotmap_compat import DotMap
     d = DotMap(coarse=DotMap(rgb=1))

@@ -7,7 +7,7 @@ import torch
 import golden_util as gu
 
 
-@pytest.mark.parametrize("name", gu.CASE_NAMES)
+@pytest.mark.parametrize("name", gu.ORACLE_CASE_NAMES)
 def test_state_matches_reference(name):
     case = gu.load_case(name)
     st = gu.oracle_state(case)
@@ -16,7 +16,7 @@ def test_state_matches_reference(name):
     assert torch.equal(st["c"].reshape(-1), case["ref"]["ref_state_c"].reshape(-1))
 
 
-@pytest.mark.parametrize("name", gu.CASE_NAMES)
+@pytest.mark.parametrize("name", gu.ORACLE_CASE_NAMES)
 def test_field_matches_reference(name):
     case = gu.load_case(name)
     st = gu.oracle_state(case)
@@ -28,7 +28,7 @@ def test_field_matches_reference(name):
         assert ((out - ref[key]).abs() / scale).max() < 2e-5
 
 
-@pytest.mark.parametrize("name", gu.CASE_NAMES)
+@pytest.mark.parametrize("name", gu.ORACLE_CASE_NAMES)
 def test_render_matches_reference(name):
     case = gu.load_case(name)
     res = gu.oracle_render(case)
@@ -81,3 +81,35 @@ def test_oracle_frames_u8_fixture():
     z = np.load(gu.GOLD + "/frames_u8.npz")
     assert np.array_equal(gu.oracle.frames_u8(torch.from_numpy(z["rgb"])), z["u8"])
     assert z["u8"].reshape(-1)[:4].tolist() == [0, 255, 255, 127]
+
+
+def test_sb2_d_is_not_degenerate():
+    ref = gu.load_case("sb2_d")["ref"]
+    assert ref["coarse_rgb"].std() > 0.1 and ref["fine_rgb"].std() > 0.1 and ref["fine_weights"].max() > 0.5
+
+
+@pytest.mark.parametrize("name", gu.GRAD_CASE_NAMES)
+def test_backward_oracle_matches_reference_gradients(name):
+    """SURVEY 8f-1 groundwork: autograd through the oracle's training loss (train/train.py:199-215) reproduces the
+    gradients the reference itself computes for every MLP parameter and the latent, incl. the path from the fine
+    loss through the depth-centred samples into the coarse MLP (nerf.py:289-291 does not detach the depth)."""
+    case, g = gu.load_case(name), gu.load_grad_case(name)
+    cfg = case["cfg"]
+    lat = case["latent"].clone().requires_grad_(True)
+    wc = {k: v.clone().requires_grad_(True) for k, v in case["wc"].items()}
+    wf = None if case["wf"] is None else {k: v.clone().requires_grad_(True) for k, v in case["wf"].items()}
+    loss = gu.oracle.train_loss(case["rays"], g["rgb_gt"], case["noise"], gu.oracle_state(case), lat, wc, wf,
+                                cfg["NS"], cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"],
+                                white_bkgd=bool(cfg["white_bkgd"]), eval_batch_size=cfg["eval_batch_size"])
+    assert abs(loss.item() - g["loss"]) < 1e-6
+    loss.backward()
+
+    def close(a, ref):
+        return (a - ref).abs().max() <= 1e-4 * ref.abs().max() + 1e-9
+
+    assert g["g_latent"].abs().max() > 0 and close(lat.grad, g["g_latent"])
+    for k, ref in g["gc"].items():
+        assert close(wc[k].grad, ref), ("coarse", k)
+    for k, ref in g["gf"].items():
+        assert close(wf[k].grad, ref), ("fine", k)
+    assert g["gc"]["blocks.4.fc_1.weight"].abs().max() > 0 and g["gf"]["lin_in.weight"].abs().max() > 0
