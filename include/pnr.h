@@ -163,6 +163,18 @@ int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, c
                    float* out, int64_t P, int32_t engine, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Backward of pnr_field_eval (what autograd does for PixelNeRFNet.forward in the reference's training step,
+ * train/train.py:199-215): d_out [SB][P][4] w.r.t. (sigmoid rgb, relu sigma) ->
+ *   grad          : a PnrMlp whose weight pointers are WRITABLE gradient buffers of the same shapes; accumulated (+=)
+ *   d_latent_nhwc : [V][Hl][Wl][C] channels-last gradient of the latent; accumulated (+=); may be NULL
+ *   d_xyz         : [SB][P][3] gradient of the sample positions (overwritten); may be NULL
+ * fp32 SIMT recompute-in-backward (first path; arithmetic = oracle/pnr_backward.py).  Not yet validated on a GPU:
+ * nothing in the default product path calls it. */
+size_t pnr_field_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P);
+int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, const float* viewdirs,
+                       const float* d_out, const PnrMlp* grad, float* d_latent_nhwc, float* d_xyz, int64_t P,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* NeRFRenderer.forward (nerf.py:251-303) with the model call inlined:
  * sample_coarse -> composite(coarse) -> sample_fine(+depth) -> sort -> composite(fine).
  * rays [SB][B][8]; mlp_fine may be NULL (then mlp_coarse is used, models.py:242). */

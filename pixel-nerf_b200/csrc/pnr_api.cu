@@ -215,6 +215,34 @@ int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, c
                         workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t pnr_field_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P) {
+  if (!scene || !mlp || P < 0) return 0;
+  return field_backward_workspace_bytes(*scene, *mlp, P * scene->SB);
+}
+
+int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, const float* viewdirs,
+                       const float* d_out, const PnrMlp* grad, float* d_latent_nhwc, float* d_xyz, int64_t P,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_scene(scene))) return rc;
+  if ((rc = check_mlp(mlp))) return rc;
+  if ((rc = check_mlp(grad))) return rc;
+  PNR_CHECK_ARG(grad->d_hidden == mlp->d_hidden && grad->n_blocks == mlp->n_blocks && grad->d_in == mlp->d_in &&
+                    grad->d_latent == mlp->d_latent && grad->combine_layer == mlp->combine_layer,
+                "grad must have the shape of mlp");
+  PNR_CHECK_ARG(P >= 0, "P must be >= 0");
+  if (P == 0) return PNR_OK;
+  PNR_CHECK_ARG(xyz && viewdirs && d_out && workspace, "NULL pointer");
+  PointSource src{};
+  src.mode = 0;
+  src.xyz = xyz;
+  src.dirs = viewdirs;
+  src.P = P;
+  src.K = 1;
+  return field_backward(*scene, *mlp, src, P * scene->SB, d_out, *grad, d_latent_nhwc, d_xyz, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
 size_t pnr_render_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
                                   const PnrRenderCfg* cfg, int64_t B) {
   if (!scene || !mlp_coarse || !cfg || B < 0) return 0;

@@ -98,6 +98,12 @@ size_t simt_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total
 int simt_field_eval(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src, int64_t total_points,
                     float* out, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// ---- field backward, SIMT first path (pnr_field_bwd.cu) --------------------------------
+size_t field_backward_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);
+int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src, int64_t total_points,
+                   const float* d_out, const PnrMlp& grad, float* d_latent, float* d_xyz, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+
 // ---- tensor engine (pnr_field_tc.cu) ---------------------------------------------------
 bool tc_supported(const PnrScene& sc, const PnrMlp& mlp);
 size_t tc_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);

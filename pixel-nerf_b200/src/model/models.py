@@ -232,7 +232,15 @@ class PixelNeRFNet(torch.nn.Module):
         """xyz (SB,B,3) world points, viewdirs (SB,B,3) -> (SB,B,4) [sigmoid rgb, relu sigma]."""
         assert viewdirs is not None, "use_viewdirs models need viewdirs"
         if self._needs_autograd(xyz, viewdirs):
+            if os.environ.get("PNR_FUSED_BACKWARD", "0") == "1" and xyz.is_cuda:
+                # opt-in until validated on a GPU: fused forward + pnr_field_backward (model/fused_field.py)
+                from .fused_field import fused_field
+                return fused_field(self, xyz, coarse, viewdirs)
             return self._forward_autograd(xyz, coarse, viewdirs)
+        return self._field_fused(xyz, coarse, viewdirs)
+
+    def _field_fused(self, xyz, coarse, viewdirs):
+        """pnr_field_eval on detached inputs (no autograd graph)."""
         SB, B, _ = xyz.shape
         use_fine = (not coarse) and self.mlp_fine is not None
         scene, mc, mf, keep = self._scene_struct(want_fine=use_fine)

@@ -81,6 +81,10 @@ def lib():
     L.pnr_field_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), i64, i32]
     L.pnr_field_workspace_bytes.restype = sz
     L.pnr_field_eval.argtypes = [P(PnrScene), P(PnrMlp), vp, vp, vp, i64, i32, vp, sz, vp]
+    L.pnr_field_backward_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), i64]
+    L.pnr_field_backward_workspace_bytes.restype = sz
+    L.pnr_field_backward.argtypes = [P(PnrScene), P(PnrMlp), vp, vp, vp, P(PnrMlp), vp, vp, i64, vp, sz, vp]
+    L.pnr_field_backward.restype = C.c_int
     L.pnr_render_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), i64]
     L.pnr_render_workspace_bytes.restype = sz
     L.pnr_render.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), vp, P(PnrNoise),
