@@ -28,6 +28,12 @@ oracle = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(oracle)
 
 
+def _mm(a, b):
+    """Every GEMM of the backward goes through here (scripts/precision_study_backward.py swaps in reduced-precision
+    emulations to size the tensor-core version)."""
+    return a @ b
+
+
 # ----------------------------------------------------------------------------------------
 # compositing (nerf.py:178-182, 222-249)
 # ----------------------------------------------------------------------------------------
@@ -148,28 +154,28 @@ def field_backward(sv, d_out):
     d_o4 = torch.cat((d_out[..., :3] * rgb * (1 - rgb), d_out[..., 3:4] * (o4[..., 3:4] > 0).float()), -1).reshape(-1, 4)
     g = {}
     h_last = sv["h_last"]
-    g["lin_out.weight"] = d_o4.t() @ torch.relu(h_last)
+    g["lin_out.weight"] = _mm(d_o4.t(), torch.relu(h_last))
     g["lin_out.bias"] = d_o4.sum(0)
-    d_h = (d_o4 @ w["lin_out.weight"]) * (h_last > 0).float()
+    d_h = _mm(d_o4, w["lin_out.weight"]) * (h_last > 0).float()
     d_lat = torch.zeros_like(sv["lat"])
     for b in range(nb - 1, -1, -1):
         s = sv["blocks"][b]
-        g[f"blocks.{b}.fc_1.weight"] = d_h.t() @ s["r"]
+        g[f"blocks.{b}.fc_1.weight"] = _mm(d_h.t(), s["r"])
         g[f"blocks.{b}.fc_1.bias"] = d_h.sum(0)
-        d_n = (d_h @ w[f"blocks.{b}.fc_1.weight"]) * (s["n"] > 0).float()
-        g[f"blocks.{b}.fc_0.weight"] = d_n.t() @ s["a"]
+        d_n = _mm(d_h, w[f"blocks.{b}.fc_1.weight"]) * (s["n"] > 0).float()
+        g[f"blocks.{b}.fc_0.weight"] = _mm(d_n.t(), s["a"])
         g[f"blocks.{b}.fc_0.bias"] = d_n.sum(0)
-        d_h = d_h + (d_n @ w[f"blocks.{b}.fc_0.weight"]) * (s["h_pre"] > 0).float()
+        d_h = d_h + _mm(d_n, w[f"blocks.{b}.fc_0.weight"]) * (s["h_pre"] > 0).float()
         if b < cl:
-            g[f"lin_z.{b}.weight"] = d_h.t() @ sv["lat"]
+            g[f"lin_z.{b}.weight"] = _mm(d_h.t(), sv["lat"])
             g[f"lin_z.{b}.bias"] = d_h.sum(0)
-            d_lat = d_lat + d_h @ w[f"lin_z.{b}.weight"]
+            d_lat = d_lat + _mm(d_h, w[f"lin_z.{b}.weight"])
         if b == cl and NS > 1:                           # mean over views (util.py:461-471)
             d = d_h.shape[-1]
             d_h = (d_h.reshape(SB, 1, P, d) / NS).expand(-1, NS, -1, -1).reshape(-1, d)
-    g["lin_in.weight"] = d_h.t() @ sv["feat"]
+    g["lin_in.weight"] = _mm(d_h.t(), sv["feat"])
     g["lin_in.bias"] = d_h.sum(0)
-    d_feat = d_h @ w["lin_in.weight"]                    # (rows, 42)
+    d_feat = _mm(d_h, w["lin_in.weight"])                    # (rows, 42)
     # positional encoding (code.py:30-42): channels [x(3), sin(x f_k + ph_k) for k in 0..11 (3 each)], then 3 view dirs
     f, ph = _posenc_tables()
     xr = sv["x_rot"]
