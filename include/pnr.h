@@ -168,12 +168,30 @@ int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, c
  *   grad          : a PnrMlp whose weight pointers are WRITABLE gradient buffers of the same shapes; accumulated (+=)
  *   d_latent_nhwc : [V][Hl][Wl][C] channels-last gradient of the latent; accumulated (+=); may be NULL
  *   d_xyz         : [SB][P][3] gradient of the sample positions (overwritten); may be NULL
- * fp32 SIMT recompute-in-backward (first path; arithmetic = oracle/pnr_backward.py).  Not yet validated on a GPU:
- * nothing in the default product path calls it. */
+ * fp32 SIMT recompute-in-backward (first path; arithmetic = oracle/pnr_backward.py).  Verified on the host emulator
+ * (tests/cuda_emu), not yet run on a GPU: nothing in the default product path calls it. */
 size_t pnr_field_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P);
 int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, const float* viewdirs,
                        const float* d_out, const PnrMlp* grad, float* d_latent_nhwc, float* d_xyz, int64_t P,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of pnr_render for a loss on the two rgb outputs (train/train.py:199-215: MSE coarse + MSE fine), i.e. what
+ * loss.backward() does below `render_par(all_rays, want_weights=True)`:
+ *   fwd          : the forward call's outputs that the backward needs: z_coarse, z_fine (sorted), depth_coarse
+ *   d_rgb_*      : [SB*B][3] upstream gradients (d_rgb_fine NULL when n_fine == 0)
+ *   grad_*       : writable PnrMlp-shaped gradient buffers, accumulated (+=); grad_fine NULL when mlp_fine is NULL
+ *   d_latent_nhwc: [V][Hl][Wl][C], accumulated (+=); may be NULL
+ * The coarse weights are detached for importance sampling but the coarse depth is not (nerf.py:286-291), so the fine
+ * loss also reaches the coarse MLP.  Gradients w.r.t. the depth / weights outputs are not supported.
+ * fp32 SIMT; arithmetic = oracle/pnr_backward.py::train_loss_backward.  Verified on the host emulator
+ * (tests/cuda_emu) against the reference's own gradients; not yet run on a GPU. */
+size_t pnr_render_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse,
+                                           const PnrMlp* mlp_fine, const PnrRenderCfg* cfg, int64_t B);
+int pnr_render_backward(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
+                        const PnrRenderCfg* cfg, const float* rays, const PnrNoise* noise,
+                        const PnrRenderOut* fwd, const float* d_rgb_coarse, const float* d_rgb_fine,
+                        const PnrMlp* grad_coarse, const PnrMlp* grad_fine, float* d_latent_nhwc, int64_t B,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* NeRFRenderer.forward (nerf.py:251-303) with the model call inlined:
  * sample_coarse -> composite(coarse) -> sample_fine(+depth) -> sort -> composite(fine).

@@ -243,6 +243,96 @@ int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xy
                         workspace_bytes, (cudaStream_t)stream);
 }
 
+static size_t render_bwd_field_ws(const PnrScene& sc, const PnrMlp& m, int64_t pts) {
+  size_t a = simt_workspace_bytes(sc, m, pts), b = field_backward_workspace_bytes(sc, m, pts);
+  return a > b ? a : b;
+}
+
+size_t pnr_render_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
+                                           const PnrRenderCfg* cfg, int64_t B) {
+  if (!scene || !mlp_coarse || !cfg || B < 0) return 0;
+  const int64_t R = B * scene->SB;
+  const int K = cfg->n_coarse + cfg->n_fine;
+  size_t b = 0;
+  b += align_up((size_t)R * K * 4 * 4, 256) * 2;   // field, d_field
+  b += align_up((size_t)R * K * 4, 256);           // d_z
+  b += align_up((size_t)R * K * 3 * 4, 256);       // d_xyz
+  b += align_up((size_t)R * 4, 256);               // d_depth
+  size_t f = render_bwd_field_ws(*scene, *mlp_coarse, R * K);
+  if (mlp_fine) {
+    size_t f2 = render_bwd_field_ws(*scene, *mlp_fine, R * K);
+    if (f2 > f) f = f2;
+  }
+  return b + f + 4096;
+}
+
+int pnr_render_backward(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
+                        const PnrRenderCfg* cfg, const float* rays, const PnrNoise* noise, const PnrRenderOut* fwd,
+                        const float* d_rgb_coarse, const float* d_rgb_fine, const PnrMlp* grad_coarse,
+                        const PnrMlp* grad_fine, float* d_latent_nhwc, int64_t B, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_scene(scene))) return rc;
+  if ((rc = check_mlp(mlp_coarse))) return rc;
+  if ((rc = check_mlp(grad_coarse))) return rc;
+  if (mlp_fine && (rc = check_mlp(mlp_fine))) return rc;
+  if (mlp_fine && (rc = check_mlp(grad_fine))) return rc;
+  PNR_CHECK_ARG(cfg && noise && fwd, "cfg / noise / fwd is NULL");
+  PNR_CHECK_ARG(cfg->n_coarse >= 1 && cfg->n_fine >= 0 && cfg->n_fine_depth >= 0 &&
+                    cfg->n_fine_depth <= cfg->n_fine,
+                "bad sample counts");
+  PNR_CHECK_ARG(B >= 0, "B must be >= 0");
+  const int64_t R = B * scene->SB;
+  if (R == 0) return PNR_OK;
+  const int Kc = cfg->n_coarse, Kf = cfg->n_fine, Kfd = cfg->n_fine_depth, K = Kc + Kf;
+  PNR_CHECK_ARG(rays && workspace && d_rgb_coarse && fwd->z_coarse, "NULL pointer (rays, workspace, d_rgb_coarse, z_coarse)");
+  if (Kf > 0) PNR_CHECK_ARG(d_rgb_fine && fwd->z_fine, "fine pass needs d_rgb_fine and the forward's z_fine");
+  if (Kf > 0 && Kfd > 0) PNR_CHECK_ARG(fwd->depth_coarse && noise->n_depth, "depth samples need depth_coarse and n_depth");
+  if (workspace_bytes < pnr_render_backward_workspace_bytes(scene, mlp_coarse, mlp_fine, cfg, B)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes,
+              pnr_render_backward_workspace_bytes(scene, mlp_coarse, mlp_fine, cfg, B));
+    return PNR_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  float* field = ar.take<float>((size_t)R * K * 4);
+  float* d_field = ar.take<float>((size_t)R * K * 4);
+  float* d_z = ar.take<float>((size_t)R * K);
+  float* d_xyz = ar.take<float>((size_t)R * K * 3);
+  float* d_depth = ar.take<float>((size_t)R);
+  char* rest = ar.base + align_up(ar.off, 256);
+  const size_t rest_bytes = workspace_bytes - align_up(ar.off, 256);
+  const bool depth_path = Kf > 0 && Kfd > 0;
+  PointSource src{};
+  src.mode = 1;
+  src.rays = rays;
+  if (Kf > 0) {   // fine pass first: it feeds d(depth_coarse) into the coarse pass (nerf.py:289-291)
+    const PnrMlp* m = mlp_fine ? mlp_fine : mlp_coarse;
+    const PnrMlp* g = mlp_fine ? grad_fine : grad_coarse;
+    src.z = fwd->z_fine;
+    src.K = K;
+    src.P = B * K;
+    if ((rc = simt_field_eval(*scene, *m, src, R * K, field, rest, rest_bytes, s))) return rc;
+    if ((rc = launch_composite_bwd(rays, fwd->z_fine, field, d_rgb_fine, nullptr, cfg->white_bkgd, d_field, d_z, R, K, s)))
+      return rc;
+    if ((rc = field_backward(*scene, *m, src, R * K, d_field, *g, d_latent_nhwc, depth_path ? d_xyz : nullptr, rest,
+                             rest_bytes, s)))
+      return rc;
+    if (depth_path &&
+        (rc = launch_depth_grad(rays, fwd->z_fine, fwd->depth_coarse, noise->n_depth, cfg->depth_std, d_z, d_xyz,
+                                d_depth, R, K, Kfd, s)))
+      return rc;
+  }
+  src.z = fwd->z_coarse;
+  src.K = Kc;
+  src.P = B * Kc;
+  if ((rc = simt_field_eval(*scene, *mlp_coarse, src, R * Kc, field, rest, rest_bytes, s))) return rc;
+  if ((rc = launch_composite_bwd(rays, fwd->z_coarse, field, d_rgb_coarse, depth_path ? d_depth : nullptr,
+                                 cfg->white_bkgd, d_field, d_z, R, Kc, s)))
+    return rc;
+  return field_backward(*scene, *mlp_coarse, src, R * Kc, d_field, *grad_coarse, d_latent_nhwc, nullptr, rest, rest_bytes, s);
+}
+
 size_t pnr_render_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
                                   const PnrRenderCfg* cfg, int64_t B) {
   if (!scene || !mlp_coarse || !cfg || B < 0) return 0;

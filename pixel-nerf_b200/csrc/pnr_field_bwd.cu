@@ -12,6 +12,8 @@
 // STATUS: compiles for sm_100a and is exported through the C ABI, but has NOT yet been run on a GPU (the round's GPU
 // budget was spent before it was written).  Nothing in the default product path calls it; tests/test_gpu_backward.py
 // is skipped unless PNR_TEST_BACKWARD=1.
+#include <stdlib.h>
+
 #include "pnr_geom.cuh"
 
 namespace pnr {
@@ -235,7 +237,12 @@ __global__ void k_geom_bwd(PnrScene sc, PointSource src, int64_t g0, int64_t n_p
 }
 
 static int64_t chunk_points(const PnrScene& sc, int64_t total_points) {
-  int64_t c = 16384 / sc.NS;  // rows per chunk <= 16384
+  int64_t rows = 16384;       // rows per chunk
+  if (const char* e = getenv("PNR_BWD_CHUNK_ROWS")) {   // test hook: force several chunks on small inputs
+    const long v = atol(e);
+    if (v >= sc.NS) rows = v;
+  }
+  int64_t c = rows / sc.NS;
   if (c > total_points) c = total_points;
   return c < 1 ? 1 : c;
 }

@@ -329,4 +329,122 @@ int launch_frames_u8(const float* rgb, int64_t n, uint8_t* out, cudaStream_t s) 
   return PNR_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// Backward of the renderer's own arithmetic (oracle/pnr_backward.py::composite_backward and the sample plumbing of
+// train_loss_backward).  One thread per ray; two sweeps over the K samples instead of storing per-sample state:
+// sweep 1 accumulates S = sum_k g_k w_k, sweep 2 turns the running prefix into the transmittance suffix sums.
+// ----------------------------------------------------------------------------------------
+__global__ void k_composite_bwd(const float* __restrict__ rays, const float* __restrict__ z,
+                                const float* __restrict__ field, const float* __restrict__ d_rgb,
+                                const float* __restrict__ d_depth, int white, float* __restrict__ d_field,
+                                float* __restrict__ d_z, int64_t R, int K) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float far = rays[r * 8 + 7];
+  const float* zr = z + r * K;
+  const float4* fr = reinterpret_cast<const float4*>(field) + r * K;
+  const float gr = d_rgb[r * 3 + 0], gg = d_rgb[r * 3 + 1], gb = d_rgb[r * 3 + 2];
+  const float gd = d_depth ? d_depth[r] : 0.f;
+  const float gbg = white ? (gr + gg + gb) : 0.f;   // rgb += 1 - sum w  (nerf.py:241-244)
+  float S = 0.f;
+  {
+    float T = 1.0f, zk = zr[0];
+    for (int k = 0; k < K; ++k) {
+      const float znext = (k + 1 < K) ? zr[k + 1] : far;
+      const float4 f = fr[k];
+      const float alpha = 1.0f - expf(-(znext - zk) * fmaxf(f.w, 0.f));
+      const float gw = ((gr * f.x + gg * f.y) + gb * f.z) + gd * zk - gbg;
+      S += gw * (alpha * T);
+      T = T * ((1.0f - alpha) + 1e-10f);
+      zk = znext;
+    }
+  }
+  float T = 1.0f, zk = zr[0], prefix = 0.f, carry = 0.f;
+  float4* dfr = reinterpret_cast<float4*>(d_field) + r * K;
+  for (int k = 0; k < K; ++k) {
+    const float znext = (k + 1 < K) ? zr[k + 1] : far;
+    const float delta = znext - zk;
+    const float4 f = fr[k];
+    const float sg = fmaxf(f.w, 0.f);
+    const float e = expf(-delta * sg);
+    const float alpha = 1.0f - e;
+    const float t = (1.0f - alpha) + 1e-10f;
+    const float w = alpha * T;
+    const float gw = ((gr * f.x + gg * f.y) + gb * f.z) + gd * zk - gbg;
+    prefix += gw * w;
+    const float d_a = gw * T - (S - prefix) / t;      // S - prefix = sum_{m>k} g_m w_m
+    const float d_delta = d_a * e * sg;
+    float4 o;
+    o.x = w * gr; o.y = w * gg; o.z = w * gb;
+    o.w = (f.w > 0.f) ? d_a * e * delta : 0.f;
+    dfr[k] = o;
+    d_z[r * K + k] = (w * gd - d_delta) + carry;       // delta_{k-1} = z_k - z_{k-1} gives +d_delta_{k-1}
+    carry = d_delta;
+    T = T * t;
+    zk = znext;
+  }
+}
+
+int launch_composite_bwd(const float* rays, const float* z, const float* field, const float* d_rgb,
+                         const float* d_depth, int white, float* d_field, float* d_z, int64_t R, int K,
+                         cudaStream_t s) {
+  if (R == 0) return PNR_OK;
+  k_composite_bwd<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(rays, z, field, d_rgb, d_depth, white, d_field, d_z, R, K);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
+// d_z[ray][k] += d_xyz[ray][k] . dir[ray]      (points = o + z d, nerf.py:185)
+__global__ void k_dz_from_dxyz(float* __restrict__ d_z, const float* __restrict__ d_xyz,
+                               const float* __restrict__ rays, int64_t R, int K) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * K) return;
+  const float* rr = rays + (i / K) * 8;
+  d_z[i] += (d_xyz[i * 3 + 0] * rr[3] + d_xyz[i * 3 + 1] * rr[4]) + d_xyz[i * 3 + 2] * rr[5];
+}
+
+// Gradient of the coarse depth through the depth-centred fine samples (nerf.py:150-161, 289-295): each sample
+// z_j = clamp(depth + n_j * std, near, far) sits somewhere in the sorted merged row; its slot is recomputed with the
+// forward's rank rule (smaller values first, ties by original index, the depth samples being the last index group).
+__global__ void k_depth_grad(const float* __restrict__ rays, const float* __restrict__ z_sorted,
+                             const float* __restrict__ depth, const float* __restrict__ nd, float depth_std,
+                             const float* __restrict__ d_z, float* __restrict__ d_depth, int64_t R, int K, int Kfd) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float near = rays[r * 8 + 6], far = rays[r * 8 + 7], d = depth[r];
+  const float* zs = z_sorted + r * K;
+  float acc = 0.f;
+  for (int j = 0; j < Kfd; ++j) {
+    const float zz = d + nd[r * Kfd + j] * depth_std;
+    if (!(zz >= near && zz <= far)) continue;            // clamped: no gradient
+    const float v = fmaxf(fminf(zz, far), near);
+    int lo = 0, hi = K;                                  // lower bound: first slot with value >= v
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (zs[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int ub = lo;
+    while (ub < K && zs[ub] == v) ++ub;
+    int n_eq_depth = 0, n_eq_before = 0;
+    for (int q = 0; q < Kfd; ++q) {
+      const float zq = fmaxf(fminf(d + nd[r * Kfd + q] * depth_std, far), near);
+      if (zq == v) { ++n_eq_depth; if (q < j) ++n_eq_before; }
+    }
+    const int pos = lo + ((ub - lo) - n_eq_depth) + n_eq_before;
+    if (pos >= 0 && pos < K) acc += d_z[r * K + pos];
+  }
+  d_depth[r] = acc;
+}
+
+int launch_depth_grad(const float* rays, const float* z_sorted, const float* depth, const float* nd,
+                      float depth_std, float* d_z, const float* d_xyz, float* d_depth, int64_t R, int K, int Kfd,
+                      cudaStream_t s) {
+  if (R == 0) return PNR_OK;
+  k_dz_from_dxyz<<<(unsigned)((R * K + 255) / 256), 256, 0, s>>>(d_z, d_xyz, rays, R, K);
+  PNR_LAUNCH_CHECK();
+  k_depth_grad<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(rays, z_sorted, depth, nd, depth_std, d_z, d_depth, R, K, Kfd);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
 }  // namespace pnr

@@ -57,16 +57,8 @@ class PnrRenderOut(C.Structure):
 _lib = None
 
 
-def lib():
-    """Loads the shared library once; raises (never falls back) if it is absent."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"libpnr_sm100.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
-            "g.build()'` (or `make -C pixel-nerf_b200/csrc`). There is no CPU fallback for the render path.")
-    L = C.CDLL(LIB_PATH)
+def declare(L):
+    """ctypes signatures of every include/pnr.h entry point on a loaded library handle."""
     L.pnr_abi_version.restype = C.c_int
     L.pnr_last_error.restype = C.c_char_p
     L.pnr_launch_count.restype = C.c_int64
@@ -85,6 +77,11 @@ def lib():
     L.pnr_field_backward_workspace_bytes.restype = sz
     L.pnr_field_backward.argtypes = [P(PnrScene), P(PnrMlp), vp, vp, vp, P(PnrMlp), vp, vp, i64, vp, sz, vp]
     L.pnr_field_backward.restype = C.c_int
+    L.pnr_render_backward_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), i64]
+    L.pnr_render_backward_workspace_bytes.restype = sz
+    L.pnr_render_backward.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), vp, P(PnrNoise),
+                                      P(PnrRenderOut), vp, vp, P(PnrMlp), P(PnrMlp), vp, i64, vp, sz, vp]
+    L.pnr_render_backward.restype = C.c_int
     L.pnr_render_workspace_bytes.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), i64]
     L.pnr_render_workspace_bytes.restype = sz
     L.pnr_render.argtypes = [P(PnrScene), P(PnrMlp), P(PnrMlp), P(PnrRenderCfg), vp, P(PnrNoise),
@@ -104,6 +101,19 @@ def lib():
                  "pnr_field_eval", "pnr_render", "pnr_pack_mlp", "pnr_project_latent", "pnr_gen_rays",
                  "pnr_frames_u8"):
         getattr(L, name).restype = C.c_int
+    return L
+
+
+def lib():
+    """Loads the shared library once; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libpnr_sm100.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C pixel-nerf_b200/csrc`). There is no CPU fallback for the render path.")
+    L = declare(C.CDLL(LIB_PATH))
     if L.pnr_abi_version() != 2:
         raise RuntimeError("libpnr_sm100.so ABI version mismatch")
     _lib = L
