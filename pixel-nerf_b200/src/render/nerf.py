@@ -15,6 +15,7 @@ the derived device state per GPU (refreshed only when encode()/weights change) a
 rays with torch.chunk semantics, so ray order in the gathered output is identical.
 """
 import copy
+import os
 
 import torch
 
@@ -193,7 +194,16 @@ class NeRFRenderer(torch.nn.Module):
         assert rays.dim() == 3
         if self._can_fuse(model, rays):
             return self._forward_fused(model, rays, want_weights)
+        if os.environ.get("PNR_FUSED_BACKWARD", "0") == "2" and rays.is_cuda and self._is_pixelnerf(model):
+            # opt-in until validated on a GPU: one autograd node, pnr_render forward + pnr_render_backward
+            from .fused_train import fused_render_train
+            return fused_render_train(self, model, rays, want_weights)
         return self._forward_torch(model, rays, want_weights)
+
+    @staticmethod
+    def _is_pixelnerf(model):
+        from model.models import PixelNeRFNet
+        return isinstance(model, PixelNeRFNet)
 
     def _can_fuse(self, model, rays):
         from model.models import PixelNeRFNet

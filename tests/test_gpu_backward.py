@@ -20,8 +20,10 @@ def rel(a, ref):
 
 
 def training_step(case, gt, fused):
+    """fused: False = composed torch, 1 = field-level node (pnr_field_backward), 2 = render-level node
+    (pnr_render + pnr_render_backward)."""
     import gpu_util
-    os.environ["PNR_FUSED_BACKWARD"] = "1" if fused else "0"
+    os.environ["PNR_FUSED_BACKWARD"] = str(int(fused))
     net = gpu_util.build_net(case, device="cuda:0", engine="simt").train()
     net.encoder.latent = case["latent"].cuda().clone().requires_grad_(True)
     renderer = gpu_util.build_renderer(case).train()
@@ -36,13 +38,14 @@ def training_step(case, gt, fused):
     return loss.item(), net
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", gu.GRAD_CASE_NAMES)
-def test_fused_backward_matches_composed_torch_on_the_same_device(name):
+def test_fused_backward_matches_composed_torch_on_the_same_device(name, mode):
     """Same device RNG for both runs, so the samples are identical and only the backward differs."""
     case, g = gu.load_case(name), gu.load_grad_case(name)
     try:
         l0, ref = training_step(case, g["rgb_gt"], fused=False)
-        l1, net = training_step(case, g["rgb_gt"], fused=True)
+        l1, net = training_step(case, g["rgb_gt"], fused=mode)
     finally:
         os.environ["PNR_FUSED_BACKWARD"] = "0"
     assert abs(l0 - l1) < 1e-5
