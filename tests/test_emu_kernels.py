@@ -71,10 +71,12 @@ def test_emulated_render_matches_oracle():
     assert (t["rgb_fine"] - ref["fine"]["rgb"])[~flipped].abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("name,chunk_rows", [("tiny", 0), ("sb2_d", 0), ("sb2_d", 24), ("ns1_coarse_only", 0)])
+@pytest.mark.parametrize("name,chunk_rows", [("tiny", 0), ("sb2_d", 0), ("sb2_d", 24), ("ns1_coarse_only", 0),
+                                             ("c2_small", 0), ("c4_small", 48)])
 def test_emulated_field_backward_matches_oracle_formulas(name, chunk_rows, monkeypatch):
     """chunk_rows > 0 forces several point chunks (gradient accumulation across chunks); ns1_coarse_only is the
-    single-view case (no view mean) with d_hidden = 128."""
+    single-view case (no view mean) with d_hidden = 128; c2_small / c4_small are the shipped d_hidden = 512 with 2 / 3
+    views (several SGEMM tiles in every dimension), c4_small with an explicit principal point."""
     if chunk_rows:
         monkeypatch.setenv("PNR_BWD_CHUNK_ROWS", str(chunk_rows))
     case = gu.load_case(name)
@@ -190,3 +192,26 @@ def test_emulated_training_step_gradients(name):
             assert rel(g_c[k], v) < 5e-4, ("coarse vs reference", k)
         for k, v in g["gf"].items():
             assert rel(g_f[k], v) < 5e-4, ("fine vs reference", k)
+
+
+def test_emulated_caller_side_and_layout_kernels():
+    """k_gen_rays (warp shuffles), k_frames_u8, k_pack_latent (shared-memory transpose) on the emulator against the
+    reference-generated fixtures / plain torch."""
+    import numpy as np
+    L = eu.lib()
+    z = np.load(gu.GOLD + "/util_rays.npz")
+    poses = torch.from_numpy(z["poses"]).contiguous()
+    for first, count in ((0, 3 * 9 * 12), (7, 100), (300, 24)):
+        rays = torch.empty(count, 8)
+        eu.ok(L.pnr_gen_rays(eu.ptr(poses), 3, 12, 9, 13.5, 13.5, 6.0, 4.5, 0.8, 1.8, first, count, eu.ptr(rays), None))
+        want = torch.from_numpy(z["rays"]).reshape(-1, 8)[first:first + count]
+        assert (rays - want).abs().max() < 1e-6
+    f = np.load(gu.GOLD + "/frames_u8.npz")
+    rgb = torch.from_numpy(f["rgb"]).contiguous()
+    out = torch.empty(rgb.shape, dtype=torch.uint8)
+    eu.ok(L.pnr_frames_u8(eu.ptr(rgb), rgb.numel(), out.data_ptr(), None))
+    assert np.array_equal(out.numpy(), f["u8"])
+    lat = torch.randn(2, 48, 5, 7, generator=torch.Generator().manual_seed(1))
+    nhwc = torch.empty(2, 5, 7, 48)
+    eu.ok(L.pnr_pack_latent(eu.ptr(lat), eu.ptr(nhwc), 2, 48, 5, 7, None))
+    assert torch.equal(nhwc, lat.permute(0, 2, 3, 1).contiguous())
