@@ -102,6 +102,7 @@ class PixelNeRFNet(torch.nn.Module):
         else:
             self.num_views_per_obj = 1
         self.encoder(images)
+        self._fused.latent_key = None     # a new latent may reuse the address (and version 0) of an old one
         self.set_cameras(poses, focal, c, images.shape[-1], images.shape[-2])
 
     def set_cameras(self, poses, focal, c, width, height):
@@ -139,6 +140,7 @@ class PixelNeRFNet(torch.nn.Module):
         self.num_objs, self.num_views_per_obj = poses.shape[0], poses.shape[1]
         enc = self.encoder
         enc.latent = latent
+        self._fused.latent_key = None
         enc.latent_scaling[0] = latent.shape[-1]
         enc.latent_scaling[1] = latent.shape[-2]
         enc.latent_scaling = enc.latent_scaling / (enc.latent_scaling - 1) * 2.0
