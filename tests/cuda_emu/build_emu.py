@@ -70,6 +70,28 @@ def rewrite(text, modes):
     return LAUNCH.sub(sub, text)
 
 
+def build_asan():
+    """Same sources with -fsanitize=address -> tests/cuda_emu/_build/libpnr_emu_asan.so.  Use it as
+         ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+         PNR_EMU_LIB=tests/cuda_emu/_build/libpnr_emu_asan.so python -m pytest tests/test_emu_kernels.py
+    to get a compute-sanitizer-like memcheck of the CUDA sources on the CPU (out-of-bounds on any tensor or
+    workspace slice is reported with the .cu line)."""
+    os.makedirs(OUT, exist_ok=True)
+    texts = {u: open(os.path.join(CSRC, u)).read() for u in UNITS}
+    modes = classify(texts.values())
+    srcs = []
+    for u in UNITS:
+        dst = os.path.join(OUT, u.replace(".cu", "_asan.cpp"))
+        open(dst, "w").write(rewrite(texts[u], modes))
+        srcs.append(dst)
+    srcs.append(os.path.join(HERE, "emu_stubs.cpp"))
+    lib = os.path.join(OUT, "libpnr_emu_asan.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-omit-frame-pointer",
+                    "-fsanitize=address", "-ffp-contract=off", "-w", "-I", HERE, "-I", CSRC, "-o", lib] + srcs,
+                   check=True)
+    return lib
+
+
 def build():
     os.makedirs(OUT, exist_ok=True)
     srcs, h = [], hashlib.sha256()
@@ -97,4 +119,5 @@ def build():
 
 
 if __name__ == "__main__":
-    print(build())
+    import sys
+    print(build_asan() if "--asan" in sys.argv else build())

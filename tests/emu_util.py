@@ -18,7 +18,8 @@ def lib():
     global _emu
     if _emu is None:
         import build_emu
-        _emu = pn.declare(C.CDLL(build_emu.build()))
+        # PNR_EMU_LIB: an alternative build of the same sources (e.g. with -fsanitize=address)
+        _emu = pn.declare(C.CDLL(os.environ.get("PNR_EMU_LIB") or build_emu.build()))
     return _emu
 
 
