@@ -108,4 +108,4 @@ def test_render_frames_equals_the_reference_caller_loop():
         got = render_frames(render_par, poses, W, H, focal, z_near, z_far, ray_batch_size=bs)
     assert got.dtype == torch.uint8 and tuple(got.shape) == (NV, H, W, 3)
     assert np.array_equal(got.cpu().numpy(), want)
-    assert want.min() < 250 and want.std() > 0.5          # not a blank (all-background) frame
+    assert want.min() < 250 and want.max() > want.min()    # not a blank (all-background) or constant frame
