@@ -32,24 +32,6 @@ namespace pnr {
 int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
           bool relu_a, bool accum, cudaStream_t s);  // pnr_field_simt.cu
 
-size_t tc3_packed_bytes();
-int tc3_pack(const PnrMlp* mlp, uint8_t* base, const float* header_src, cudaStream_t s);
-size_t tc3_workspace_bytes(int pairs);
-int tc3_field_eval(const PnrScene& sc, const PnrMlp& mlp, const uint8_t* packed3, const float* proj,
-                   const PointSource& src, int64_t total_points, float* out, void* ws, int pairs, int* status,
-                   cudaStream_t s);
-
-// Which tensor-engine mapping runs: 2 = M-split pair (this file; default, fastest measured), 3 = N-split pair
-// (pnr_field_tc3.cu).  PNR_TC_VARIANT selects.
-static int tc_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PNR_TC_VARIANT");
-    v = (e && e[0] == '3') ? 3 : 2;
-  }
-  return v;
-}
-
 namespace tc {
 
 constexpr int D = 512;
@@ -760,6 +742,11 @@ static int get_status_buffer(int** out) {
   if (!g_status[dev]) {
     PNR_CUDA(cudaMalloc(&g_status[dev], 256));
     PNR_CUDA(cudaMemset(g_status[dev], 0, 256));
+    // word 0: tag of the first barrier wait that timed out; word 1: 1 = __trap() on a timeout (default: a protocol
+    // failure must kill the launch loudly instead of returning garbage with rc == PNR_OK), 0 = record the tag and
+    // carry on (PNR_TC_NO_TRAP=1, for scripts/tc_debug.py which then reads the tag with pnr_tc_status)
+    const int init[2] = {0, getenv("PNR_TC_NO_TRAP") ? 0 : 1};
+    PNR_CUDA(cudaMemcpy(g_status[dev], init, sizeof(init), cudaMemcpyHostToDevice));
   }
   *out = g_status[dev];
   return PNR_OK;
@@ -768,8 +755,10 @@ static int get_status_buffer(int** out) {
 }  // namespace tc
 
 bool tc_supported(const PnrScene& sc, const PnrMlp& m) {
+  // the kernel addresses the projected maps with 32-bit ELEMENT offsets (geo[0..3]): one map must stay below 2^32 floats
+  const unsigned long long map_elems = (unsigned long long)sc.SB * sc.NS * sc.Hl * sc.Wl * tc::D;
   return m.d_hidden == tc::D && m.d_latent == tc::D && sc.C == tc::D && m.d_in == 42 && m.d_out == 4 &&
-         m.n_blocks == 5 && m.combine_layer == 3 && sc.NS >= 1 && sc.NS <= 64;
+         m.n_blocks == 5 && m.combine_layer == 3 && sc.NS >= 1 && sc.NS <= 64 && map_elems < (1ull << 32);
 }
 
 static int tc_pairs(int64_t n_tiles) {
@@ -785,9 +774,7 @@ static size_t tc2_packed_bytes() { return (size_t)tc::HEADER_BYTES + (size_t)2 *
 
 size_t tc_workspace_bytes(const PnrScene&, const PnrMlp&, int64_t total_points) {
   int64_t n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
-  size_t a = (size_t)tc_pairs(n_tiles) * 2 * tc::D * tc::ROWS * sizeof(float) + 1024;
-  size_t b = tc3_workspace_bytes(tc_pairs(n_tiles));
-  return a > b ? a : b;
+  return (size_t)tc_pairs(n_tiles) * 2 * tc::D * tc::ROWS * sizeof(float) + 1024;
 }
 
 int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
@@ -805,14 +792,6 @@ int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, cons
     return PNR_ERR_WORKSPACE;
   }
   if (total_points == 0) return PNR_OK;
-  if (tc_variant() == 3) {
-    int* status = nullptr;
-    int rc3 = tc::get_status_buffer(&status);
-    if (rc3) return rc3;
-    const int64_t tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
-    return tc3_field_eval(sc, mlp, static_cast<const uint8_t*>(mlp.packed) + tc2_packed_bytes(), proj, src,
-                          total_points, out, ws, tc_pairs(tiles), status, s);
-  }
   tc::Params p;
   p.sc = sc;
   p.src = src;
@@ -848,7 +827,7 @@ extern "C" {
 
 size_t pnr_pack_mlp_bytes(const PnrMlp* mlp) {
   if (!mlp || mlp->d_hidden != tc::D || mlp->d_latent != tc::D || mlp->n_blocks != 5 || mlp->d_in != 42) return 0;
-  return tc2_packed_bytes() + tc3_packed_bytes();
+  return tc2_packed_bytes();
 }
 
 int pnr_pack_mlp(const PnrMlp* mlp, void* packed, size_t packed_bytes, void* stream) {
@@ -887,7 +866,7 @@ int pnr_pack_mlp(const PnrMlp* mlp, void* packed, size_t packed_bytes, void* str
     tc::k_pack_layer<<<dim3(tc::SLOTS_FC, 2), 256, 0, s>>>(mlp->fc1_w[i], tc::D, r0 + o1, r1 + o1, header);
     PNR_LAUNCH_CHECK();
   }
-  return tc3_pack(mlp, base + tc2_packed_bytes(), header, s);
+  return PNR_OK;
 }
 
 size_t pnr_project_latent_bytes(const PnrScene* sc, const PnrMlp* mlp) {
@@ -921,7 +900,8 @@ int pnr_project_latent(const PnrScene* sc, const PnrMlp* mlp, float* proj, size_
 }
 
 // Debug / test hook: synchronises the device and returns the tensor-engine status word
-// (0 = ok, otherwise the tag of the first barrier wait that timed out); clears it.
+// (0 = ok, otherwise the tag of the first barrier wait that timed out -- only observable with PNR_TC_NO_TRAP=1, by
+// default a timeout traps and every later CUDA call fails); clears it.
 int pnr_tc_status(int* out) {
   int* buf = nullptr;
   int rc = tc::get_status_buffer(&buf);

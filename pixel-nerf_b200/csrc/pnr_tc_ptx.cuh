@@ -49,6 +49,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
       if (*(volatile int*)status != 0) return;
       if (clock64() - t0 > TIMEOUT_CYCLES) {
         atomicCAS(status, 0, tag);
+        if (((volatile int*)status)[1]) __trap();   // default: fail the launch loudly (see get_status_buffer)
         return;
       }
     }
@@ -75,6 +76,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, in
       if (*(volatile int*)status != 0) break;
       if (clock64() - t0 > TIMEOUT_CYCLES) {
         atomicCAS(status, 0, tag);
+        if (((volatile int*)status)[1]) __trap();
         break;
       }
     }
@@ -271,6 +273,7 @@ static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_
       if (*(volatile int*)status != 0) return;
       if (clock64() - t0 > TIMEOUT_CYCLES) {
         atomicCAS(status, 0, tag);
+        if (((volatile int*)status)[1]) __trap();   // default: fail the launch loudly (see get_status_buffer)
         return;
       }
     }

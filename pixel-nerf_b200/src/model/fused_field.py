@@ -1,7 +1,8 @@
-"""Fused forward + `pnr_field_backward` for PixelNeRFNet.forward in grad mode (first path).
+"""Fused forward + `pnr_field_backward` for PixelNeRFNet.forward in grad mode on CUDA.
 
-Opt-in (`PNR_FUSED_BACKWARD=1`): the default grad-mode path is still the composed-torch one, whose gradients are
-pinned to the reference's (tests/test_host_logic.py).  This path has not been run on a GPU yet.
+Used whenever `net(xyz, ...)` itself is called with gradients required (a whole training step through
+`NeRFRenderer` uses the render-level node of render/fused_train.py instead; `PNR_FUSED_BACKWARD=1` forces this
+field-level node there too, `=0` the composed-torch path).  Validated on B200 (tests/test_gpu_backward.py).
 
 The autograd node takes the sample positions, the latent and the MLP parameters as inputs, so autograd carries
 `d_xyz` back into the renderer (sample depths), `d_latent` into the encoder trunk and the weight gradients into the

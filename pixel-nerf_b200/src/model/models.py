@@ -4,9 +4,10 @@ state in module buffers, `forward(xyz, coarse, viewdirs)` evaluates the conditio
 
 Inference (no autograd) goes to the fused sm_100a kernels through the C ABI
 (`pnr_field_eval`, include/pnr.h); there is no CPU fallback on that path.  When gradients are
-required (train/train.py) the field is evaluated by the composed torch ops in
-`_forward_autograd` -- the documented grad-mode path until the backward kernels exist
-(SURVEY.md section 8f row 1).
+required on CUDA (train/train.py) the same fused forward runs inside an autograd node whose
+backward is `pnr_field_backward` (model/fused_field.py).  The
+composed torch ops of `_forward_autograd` remain for CPU tensors in grad mode (host-logic
+tests) and as the PNR_FUSED_BACKWARD=0 cross-check of the gradient tests.
 """
 import os
 import os.path as osp
@@ -71,6 +72,12 @@ class PixelNeRFNet(torch.nn.Module):
 
         d_latent = self.encoder.latent_size
         self.code = PositionalEncoding.from_conf(conf["code"], d_in=3)
+        # the fused kernels (csrc/pnr_geom.cuh feat_channel, k_geom_bwd) compute THIS code in registers
+        if not (self.code.num_freqs == 6 and self.code.include_input and abs(self.code.freq_factor - 1.5) < 1e-12):
+            raise NotImplementedError(
+                "model.code must be num_freqs = 6, freq_factor = 1.5, include_input = True (every shipped conf); got "
+                f"num_freqs = {self.code.num_freqs}, freq_factor = {self.code.freq_factor}, "
+                f"include_input = {self.code.include_input}")
         d_in = self.code.d_out + 3  # + un-encoded view directions (models.py:58-60)
         d_out = 4
         self.latent_size = self.encoder.latent_size
@@ -84,6 +91,7 @@ class PixelNeRFNet(torch.nn.Module):
         self.num_objs = 0
         self.num_views_per_obj = 1
         self._image_wh = (0.0, 0.0)
+        self._scene_epoch = 0          # bumped by every encode() / set_scene() / set_cameras(): keys per-GPU replicas
         self._fused = _FusedCache()
         self.engine = os.environ.get("PNR_ENGINE", "auto")  # auto | simt | tc
 
@@ -110,7 +118,7 @@ class PixelNeRFNet(torch.nn.Module):
         also be installed from a precomputed latent (see `set_scene`)."""
         rot = poses[:, :3, :3].transpose(1, 2)
         trans = -torch.bmm(rot, poses[:, :3, 3:])
-        self.poses = torch.cat((rot, trans), dim=-1)          # world -> camera, (V,3,4)
+        self.poses = torch.cat((rot, trans), dim=-1).contiguous()          # world -> camera, (V,3,4)
         self.image_shape[0] = width
         self.image_shape[1] = height
         self._image_wh = (float(width), float(height))
@@ -121,7 +129,7 @@ class PixelNeRFNet(torch.nn.Module):
             focal = focal.unsqueeze(-1).repeat((1, 2))
         else:
             focal = focal.clone()
-        self.focal = focal.float()
+        self.focal = focal.float().contiguous()   # _scene_struct hands raw pointers of these buffers to the kernels
         self.focal[..., 1] *= -1.0
         if c is None:
             c = (self.image_shape * 0.5).unsqueeze(0)
@@ -131,7 +139,8 @@ class PixelNeRFNet(torch.nn.Module):
                 c = c[None, None].repeat((1, 2))
             elif c.dim() == 1:
                 c = c.unsqueeze(-1).repeat((1, 2))
-        self.c = c.float()
+        self.c = c.float().contiguous()
+        self._scene_epoch += 1
 
     def set_scene(self, latent, poses, focal, c, width, height):
         """Install a precomputed latent (V,L,Hl,Wl) with cameras (SB,NS,4,4) -- what encode()
@@ -234,8 +243,8 @@ class PixelNeRFNet(torch.nn.Module):
         """xyz (SB,B,3) world points, viewdirs (SB,B,3) -> (SB,B,4) [sigmoid rgb, relu sigma]."""
         assert viewdirs is not None, "use_viewdirs models need viewdirs"
         if self._needs_autograd(xyz, viewdirs):
-            if os.environ.get("PNR_FUSED_BACKWARD", "0") == "1" and xyz.is_cuda:
-                # opt-in until validated on a GPU: fused forward + pnr_field_backward (model/fused_field.py)
+            if os.environ.get("PNR_FUSED_BACKWARD", "auto") != "0" and xyz.is_cuda:
+                # fused forward + pnr_field_backward in one autograd node (model/fused_field.py)
                 from .fused_field import fused_field
                 return fused_field(self, xyz, coarse, viewdirs)
             return self._forward_autograd(xyz, coarse, viewdirs)
@@ -263,10 +272,6 @@ class PixelNeRFNet(torch.nn.Module):
             pn.check(L.pnr_field_eval(scene, m, pn.dptr(xyz_c, "xyz"), pn.dptr(dirs_c, "viewdirs"), pn.dptr(out),
                                       B, eng, ws.data_ptr(), ws.numel(), pn.stream_ptr(dev)))
         return out
-
-    def _torch_field(self, xyz, coarse=True, viewdirs=None, far=False):
-        """The composed-torch field as a plain callable (bench.py --impl torch-eager; use_viewdirs protocol)."""
-        return self._forward_autograd(xyz, coarse, viewdirs)
 
     def _forward_autograd(self, xyz, coarse, viewdirs):
         """Differentiable composed-torch evaluation (training only)."""

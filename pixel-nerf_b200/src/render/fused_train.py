@@ -1,10 +1,10 @@
-"""Fused forward + `pnr_render_backward` for a training step (first path).
+"""Fused forward + `pnr_render_backward` for a training step.
 
-Opt-in (`PNR_FUSED_BACKWARD=2`): `NeRFRenderer.forward` in grad mode becomes ONE autograd node whose forward is the
-fused `pnr_render` (any engine, incl. the tensor engine) and whose backward is `pnr_render_backward`.  The default
-grad-mode path stays the composed-torch one, whose gradients are pinned to the reference's.  The C-level backward
-reproduces the reference's gradients on the host emulator (tests/test_emu_kernels.py); this Python glue has not been
-run on a GPU yet.
+The default grad-mode path on CUDA (`PNR_FUSED_BACKWARD` unset / auto / 2): `NeRFRenderer.forward` becomes ONE autograd
+node whose forward is the fused `pnr_render` (any engine, incl. the tensor engine) and whose backward is
+`pnr_render_backward` (fp32 recompute-in-backward).  Validated on B200 against the composed-torch path on the same
+device and against the gradients the reference computed itself (tests/test_gpu_backward.py), and on the host emulator
+(tests/test_emu_kernels.py).
 
 Differentiable outputs: `coarse.rgb`, `fine.rgb` (what train/train.py:199-212 puts into the loss).  depth and
 weights are returned but carry no gradient here (the shipped losses do not use them; lambda_alpha = 0).
@@ -18,7 +18,7 @@ from .dotmap_compat import DotMap
 
 class _FusedRender(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, renderer, model, want_weights, n_coarse_params, rays, latent, *params):
+    def forward(ctx, renderer, model, want_weights, noise_in, rays, latent, *params):
         dev = rays.device
         SB, B, _ = rays.shape
         R = SB * B
@@ -27,17 +27,19 @@ class _FusedRender(torch.autograd.Function):
         if not fine:
             Kf = Kfd = 0
         f32 = dict(dtype=torch.float32, device=dev)
-        noise = {"u_coarse": torch.rand(R, Kc, **f32)}          # the reference's draw order (nerf.py:111,135,141,158)
-        if fine and Kf - Kfd > 0:
-            noise["u_fine"] = torch.rand(R, Kf - Kfd, **f32)
-            noise["u_fine_jit"] = torch.rand(R, Kf - Kfd, **f32)
-        if fine and Kfd > 0:
-            noise["n_depth"] = torch.randn(R, Kfd, **f32)
+        if noise_in is not None:          # parity tests replay a fixture's draws
+            noise = {k: v.to(**f32).contiguous() for k, v in noise_in.items()}
+        else:
+            noise = {"u_coarse": torch.rand(R, Kc, **f32)}      # the reference's draw order (nerf.py:111,135,141,158)
+            if fine and Kf - Kfd > 0:
+                noise["u_fine"] = torch.rand(R, Kf - Kfd, **f32)
+                noise["u_fine_jit"] = torch.rand(R, Kf - Kfd, **f32)
+            if fine and Kfd > 0:
+                noise["n_depth"] = torch.randn(R, Kfd, **f32)
         with torch.no_grad():
             res = renderer._forward_fused(model, rays, want_weights, noise_in=noise, want_z=True)
         ctx.renderer, ctx.model, ctx.noise = renderer, model, noise
         ctx.cfg = (Kc, Kf, Kfd, fine, float(renderer.depth_std), bool(renderer.white_bkgd))
-        ctx.n_coarse_params = n_coarse_params
         ctx.rays = rays.detach().contiguous().float()
         ctx.fwd = (res.coarse.z.reshape(R, Kc), res.fine.z.reshape(R, Kc + Kf) if fine else None,
                    res.coarse.depth.reshape(R))
@@ -109,13 +111,12 @@ class _FusedRender(torch.autograd.Function):
         return (None, None, None, None, None, g_latent) + tuple(flat)
 
 
-def fused_render_train(renderer, model, rays, want_weights):
+def fused_render_train(renderer, model, rays, want_weights, noise_in=None):
     fine = bool(renderer.using_fine) and int(renderer.n_fine) > 0
     mlps = [model.mlp_coarse] + ([model.mlp_fine] if (fine and model.mlp_fine is not None) else [])
     params = [p for mlp in mlps for _, p in mlp.named_parameters()]
     latent = model.encoder.latent.detach() if model.stop_encoder_grad else model.encoder.latent
-    outs = list(_FusedRender.apply(renderer, model, want_weights, len(list(model.mlp_coarse.parameters())),
-                                   rays, latent, *params))
+    outs = list(_FusedRender.apply(renderer, model, want_weights, noise_in, rays, latent, *params))
     res = DotMap()
     res.coarse = DotMap(rgb=outs.pop(0), depth=outs.pop(0))
     if want_weights:

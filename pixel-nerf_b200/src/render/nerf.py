@@ -6,16 +6,19 @@ rays, want_weights)`, `bind_parallel(net, gpus, simple_output)`, `sched_step`, m
 Inference with a PixelNeRFNet on CUDA runs the whole sample -> field -> composite ->
 resample -> field -> composite chain in one C-ABI call (`pnr_render`, include/pnr.h); the
 random draws are made here with torch, in the reference's order, and handed to the kernels,
-so a seeded run replays the reference's samples.  With autograd enabled (training) or a
-foreign `model` callable the renderer uses the composed torch path below.
+so a seeded run replays the reference's samples.  With autograd enabled (training) on CUDA the
+same fused forward runs inside one autograd node whose backward is `pnr_render_backward`
+(render/fused_train.py); a foreign `model` callable, CPU tensors in grad mode (host-logic
+tests) or PNR_FUSED_BACKWARD=0 use the composed torch path below.
 
 Multi-GPU (`bind_parallel(net, gpus)`): the reference wraps a `DataParallel(dim=1)`, which
-re-broadcasts the whole module on every call; `_ShardedRender` instead keeps one replica of
-the derived device state per GPU (refreshed only when encode()/weights change) and slices
-rays with torch.chunk semantics, so ray order in the gathered output is identical.
+re-broadcasts the whole module on every call; `_ShardedRender` instead keeps a `_SceneReplica`
+(peer copies of the already-derived device state) per extra GPU, refreshed only when
+encode()/weights change, and slices rays with torch.chunk semantics, so ray order in the
+gathered output is identical.
 """
-import copy
 import os
+import warnings
 
 import torch
 
@@ -61,6 +64,14 @@ def _integrate(rays, z, field, white_bkgd):
     return w, rgb, depth
 
 
+def _wrapper_output(renderer, outputs, simple_output):
+    """(rgb, depth) of the best pass, or the plain nested dict (nerf.py:31-42)."""
+    if simple_output:
+        best = outputs.fine if renderer.using_fine else outputs.coarse
+        return best.rgb, best.depth
+    return outputs.toDict()
+
+
 class _RenderWrapper(torch.nn.Module):
     """Callable returned by bind_parallel (nerf.py:15-42)."""
 
@@ -74,57 +85,102 @@ class _RenderWrapper(torch.nn.Module):
         if rays.shape[0] == 0:
             return torch.zeros(0, 3, device=rays.device), torch.zeros(0, device=rays.device)
         outputs = self.renderer(self.net, rays, want_weights=want_weights and not self.simple_output)
-        if self.simple_output:
-            best = outputs.fine if self.renderer.using_fine else outputs.coarse
-            return best.rgb, best.depth
-        return outputs.toDict()
+        return _wrapper_output(self.renderer, outputs, self.simple_output)
+
+
+class _SceneReplica:
+    """Everything the fused render path reads, on ANOTHER GPU of the same process: channels-last latent, cameras, fp32
+    weights, packed tensor-engine weights and projected maps.  Filled by peer copies (NVLink) of the primary device's
+    ALREADY DERIVED buffers -- no module deepcopy, no re-pack, no re-projection -- and refreshed only when the weights
+    (parameter versions) or the scene (`net._scene_epoch`, latent version) change.  The reference's DataParallel
+    re-broadcasts the whole module on every forward call instead (src/render/nerf.py:370)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.engine = "auto"
+        self.mlp, self.mlp_key = {}, {}
+        self.scene_key = None
+        self.refreshes = 0          # (weights, scene) copies made so far: tests and DESIGN.md quote it
+
+    def refresh(self, net, want_fine):
+        from model.models import _param_key
+        dev = self.device
+        self.engine = net.engine
+        names = ["mlp_coarse"] + (["mlp_fine"] if (want_fine and net.mlp_fine is not None) else [])
+        scene0, _, _, (nhwc0, proj0) = net._scene_struct(want_fine=want_fine)   # primary: packs / projects if stale
+        for name in names:
+            mlp = getattr(net, name)
+            key = _param_key(mlp)
+            if self.mlp_key.get(name) == key:
+                continue
+            _, _, sd0, packed0 = net._fused.mlp[name]
+            sd = {k: v.to(dev, non_blocking=True) for k, v in sd0.items()}
+            packed = packed0.to(dev, non_blocking=True) if packed0 is not None else None
+            struct = pn.make_mlp_struct(sd, mlp.d_in, mlp.d_latent, mlp.d_hidden, mlp.d_out, mlp.n_blocks,
+                                        mlp.combine_layer, packed=packed)
+            self.mlp[name], self.mlp_key[name] = (struct, sd, packed), key
+            self.refreshes += 1
+        lat = net.encoder.latent
+        skey = (net._scene_epoch, lat.data_ptr(), lat._version, tuple(self.mlp_key.get(n) for n in names), want_fine)
+        if skey != self.scene_key:
+            to = lambda t: None if t is None else t.to(dev, non_blocking=True)
+            self.nhwc = to(nhwc0)
+            self.proj = {k: to(v) for k, v in proj0.items()}
+            self.poses, self.focal, self.c = to(net.poses), to(net.focal), to(net.c)
+            self.meta = (scene0.SB, scene0.NS, scene0.image_w, scene0.image_h, scene0.scale_x, scene0.scale_y)
+            self.scene_key = skey
+            self.refreshes += 1
+
+    def _scene_struct(self, want_fine):
+        SB, NS, w, h, sx, sy = self.meta
+        mc = self.mlp["mlp_coarse"][0]
+        mf = self.mlp["mlp_fine"][0] if (want_fine and "mlp_fine" in self.mlp) else None
+        scene = pn.make_scene_struct(self.nhwc, self.poses, self.focal, self.c, SB, NS, w, h, sx, sy,
+                                     proj_coarse=self.proj.get("mlp_coarse"), proj_fine=self.proj.get("mlp_fine"))
+        return scene, mc, mf, (self.nhwc, self.proj)
 
 
 class _ShardedRender(torch.nn.Module):
-    """Single-process ray sharding over several GPUs (replaces nn.DataParallel(dim=1),
-    nerf.py:368-370).  Shard i gets torch.chunk piece i of the rays along dim 1; kernels on all
-    devices are enqueued from this thread (launches are asynchronous) and results are copied
-    to gpus[0] in shard order."""
+    """Single-process ray sharding over several GPUs (replaces nn.DataParallel(dim=1), nerf.py:368-370).  Shard i gets
+    torch.chunk piece i of the rays along dim 1 (same ray order as DataParallel); kernels on all devices are enqueued
+    from this thread (launches are asynchronous) and results are copied to gpus[0] in shard order.  GPUs other than
+    gpus[0] render from a `_SceneReplica`.
+
+    Gradient mode (train/train.py with several --gpu_id): the autograd graph lives on gpus[0], so the step runs there
+    alone (with a one-time warning) -- replicas hold detached copies and would drop the shards' gradients."""
 
     def __init__(self, wrapped, gpus):
         super().__init__()
         self.module = wrapped
         self.gpus = [int(g) for g in gpus]
-        self._replicas = {}
-        self._key = None
-
-    def _refresh(self):
-        net = self.module.net
-        key = (tuple((p.data_ptr(), p._version) for p in net.parameters()),
-               net.encoder.latent.data_ptr(), net.encoder.latent._version, net.poses.data_ptr(),
-               net.num_views_per_obj)
-        if key == self._key:
-            return
-        self._replicas = {}
-        for g in self.gpus[1:]:
-            dev = torch.device("cuda", g)
-            fused, net._fused = net._fused, None   # derived device state is rebuilt per replica
-            try:
-                rep = copy.deepcopy(net).to(dev)   # encode() buffers are registered, so they follow
-            finally:
-                net._fused = fused
-            rep._fused = type(fused)()
-            rep.num_objs, rep.num_views_per_obj = net.num_objs, net.num_views_per_obj
-            rep._image_wh = net._image_wh
-            rep.eval()
-            self._replicas[g] = _RenderWrapper(rep, self.module.renderer, self.module.simple_output)
-        self._key = key
+        self._replicas = {g: _SceneReplica(torch.device("cuda", g)) for g in self.gpus[1:]}
+        self._warned = False
 
     def forward(self, rays, want_weights=False):
-        self._refresh()
+        net, renderer, simple = self.module.net, self.module.renderer, self.module.simple_output
+        if rays.shape[0] == 0 or net._needs_autograd(rays):
+            if rays.shape[0] != 0 and not self._warned:
+                warnings.warn(f"bind_parallel(net, {self.gpus}): gradients are required, so this call runs on cuda:"
+                              f"{self.gpus[0]} only (multi-GPU training = one process per GPU)")
+                self._warned = True
+            return self.module(rays, want_weights=want_weights)
+        if renderer.sched is not None and renderer.last_sched.item() > 0:     # as NeRFRenderer.forward (nerf.py:265-267)
+            renderer.n_coarse = renderer.sched[1][renderer.last_sched.item() - 1]
+            renderer.n_fine = renderer.sched[2][renderer.last_sched.item() - 1]
+        fine = bool(renderer.using_fine) and int(renderer.n_fine) > 0
         dev0 = torch.device("cuda", self.gpus[0])
         pieces = torch.chunk(rays, len(self.gpus), dim=1)
         results = []
         for g, piece in zip(self.gpus, pieces):
-            dev = torch.device("cuda", g)
-            mod = self.module if g == self.gpus[0] else self._replicas[g]
-            with torch.cuda.device(dev):
-                results.append(mod(piece.to(dev, non_blocking=True), want_weights=want_weights))
+            if g == self.gpus[0]:
+                results.append(self.module(piece.to(dev0, non_blocking=True), want_weights=want_weights))
+                continue
+            rep = self._replicas[g]
+            rep.refresh(net, fine)
+            with torch.cuda.device(rep.device):
+                out = renderer._forward_fused(rep, piece.to(rep.device, non_blocking=True),
+                                              want_weights and not simple)
+            results.append(_wrapper_output(renderer, out, simple))
         return _gather(results, dev0)
 
 
@@ -194,8 +250,12 @@ class NeRFRenderer(torch.nn.Module):
         assert rays.dim() == 3
         if self._can_fuse(model, rays):
             return self._forward_fused(model, rays, want_weights)
-        if os.environ.get("PNR_FUSED_BACKWARD", "0") == "2" and rays.is_cuda and self._is_pixelnerf(model):
-            # opt-in until validated on a GPU: one autograd node, pnr_render forward + pnr_render_backward
+        mode = os.environ.get("PNR_FUSED_BACKWARD", "auto")
+        if (mode in ("auto", "2") and rays.is_cuda and self._is_pixelnerf(model)
+                and not (self.training and self.noise_std > 0.0)):
+            # training step on the GPU (train/train.py:199-215): ONE autograd node, pnr_render forward +
+            # pnr_render_backward (render/fused_train.py).  PNR_FUSED_BACKWARD=1 keeps the renderer in torch ops with a
+            # fused field node (model/fused_field.py); =0 is the composed-torch path the gradient tests compare with.
             from .fused_train import fused_render_train
             return fused_render_train(self, model, rays, want_weights)
         return self._forward_torch(model, rays, want_weights)

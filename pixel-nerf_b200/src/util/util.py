@@ -5,6 +5,7 @@ path are provided; image-io, colour-map and conv-padding utilities of the refere
 outside the hot path and are not part of this package.
 """
 import functools
+import math
 
 import numpy as np
 import torch
@@ -111,8 +112,9 @@ def get_cuda(gpu_id):
 
 
 def psnr(pred, target):
+    """PSNR in dB of two tensors or arrays, as a python float (util.py:474-481)."""
     mse = ((pred - target) ** 2).mean()
-    return -10 * torch.log10(mse)
+    return -10 * math.log10(mse)
 
 
 def count_parameters(model):

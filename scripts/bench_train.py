@@ -3,11 +3,12 @@
 with want_weights=True, MSE coarse + MSE fine, backward through MLPs and the encoder trunk, Adam step
 (train/train.py:117-233, SB = 4 and B = 128 are its defaults) -- through this package's classes.
 
-    python scripts/bench_train.py --mode torch      # composed-torch grad path (the default of the package)
-    python scripts/bench_train.py --mode field      # PNR_FUSED_BACKWARD=1: fused field forward + pnr_field_backward
-    python scripts/bench_train.py --mode render     # PNR_FUSED_BACKWARD=2: pnr_render + pnr_render_backward
+    python scripts/bench_train.py --mode render     # the package default: pnr_render + pnr_render_backward in one node
+    python scripts/bench_train.py --mode field      # PNR_FUSED_BACKWARD=1: torch renderer, fused field fwd + pnr_field_backward
+    python scripts/bench_train.py --mode torch      # PNR_FUSED_BACKWARD=0: composed-torch grad path of this package
+    python scripts/bench_train.py --mode reference  # the UNMODIFIED reference (baseline/_ref), same step, same GPU
 
-`--mode field/render` have not been run on a GPU yet.  `--device cpu --tiny` checks the script itself (torch mode)."""
+`--device cpu --tiny` checks the script itself (torch mode)."""
 import argparse
 import json
 import os
@@ -25,7 +26,7 @@ import synth  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", choices=["torch", "field", "render"], default="torch")
+    ap.add_argument("--mode", choices=["torch", "field", "render", "reference"], default="render")
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -33,28 +34,41 @@ def main():
     ap.add_argument("--B", type=int, default=128)
     ap.add_argument("--tiny", action="store_true", help="d_hidden 32, 8+4 samples, 32x32 images: a script self-check")
     a = ap.parse_args()
-    os.environ["PNR_FUSED_BACKWARD"] = {"torch": "0", "field": "1", "render": "2"}[a.mode]
-    import util
-    from model import make_model
-    from render import NeRFRenderer
+    os.environ["PNR_FUSED_BACKWARD"] = {"torch": "0", "field": "1", "render": "2", "reference": "0"}[a.mode]
     dev = torch.device(a.device)
-    conf = util.hocon.parse_file(os.path.join(ROOT, "pixel-nerf_b200", "conf", "exp", "srn.conf"))
-    conf.put("model.encoder.pretrained", False)
     W = H = 128
-    if a.tiny:
-        W = H = 32
-        for k in ("model.mlp_coarse.d_hidden", "model.mlp_fine.d_hidden"):
-            conf.put(k, 32)
-        conf.put("renderer.n_coarse", 8)
-        conf.put("renderer.n_fine", 4)
-        conf.put("renderer.n_fine_depth", 2)
-    torch.manual_seed(0)
-    net = make_model(conf["model"]).to(dev).train()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    if a.mode == "reference":
+        # the reference's own classes (packages `model` / `render` / `util` of baseline/_ref instead of this repo's)
+        sys.path.remove(os.path.join(ROOT, "pixel-nerf_b200", "src"))
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_harness as rh
+        model, render, _ = rh.import_reference()
+        torch.manual_seed(0)
+        net = model.make_model(rh.model_conf(512, True)).to(dev).train()
+        NeRFRenderer = render.NeRFRenderer
+        renderer = NeRFRenderer(n_coarse=64, n_fine=32, n_fine_depth=16, depth_std=0.01, white_bkgd=True).to(dev).train()
+    else:
+        import util
+        from model import make_model
+        from render import NeRFRenderer
+        conf = util.hocon.parse_file(os.path.join(ROOT, "pixel-nerf_b200", "conf", "exp", "srn.conf"))
+        conf.put("model.encoder.pretrained", False)
+        if a.tiny:
+            W = H = 32
+            for k in ("model.mlp_coarse.d_hidden", "model.mlp_fine.d_hidden"):
+                conf.put(k, 32)
+            conf.put("renderer.n_coarse", 8)
+            conf.put("renderer.n_fine", 4)
+            conf.put("renderer.n_fine_depth", 2)
+        torch.manual_seed(0)
+        net = make_model(conf["model"]).to(dev).train()
+        renderer = NeRFRenderer.from_conf(conf["renderer"], lindisp=False).to(dev).train()
     with torch.no_grad():                       # the reference zero-initialises fc_1: give every layer a gradient
         for mlp in (net.mlp_coarse, net.mlp_fine):
             for blk in mlp.blocks:
                 blk.fc_1.weight.normal_(0, 0.03)
-    renderer = NeRFRenderer.from_conf(conf["renderer"], lindisp=False).to(dev).train()
     render_par = renderer.bind_parallel(net, None).train()
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
     NS, SB, B = 2, a.SB, a.B

@@ -1,8 +1,6 @@
-"""pnr_field_backward (fp32 SIMT recompute-in-backward) against the gradients the reference produced itself
-(tests/golden/grad_*.npz) and against the composed-torch grad-mode path.
-
-NOT YET VALIDATED ON A GPU: written after the round's GPU budget was spent, so it is skipped unless
-PNR_TEST_BACKWARD=1 (the first thing to run next round)."""
+"""pnr_field_backward / pnr_render_backward (fp32 SIMT recompute-in-backward; the default training path on CUDA) against
+the gradients the reference produced itself (tests/golden/grad_*.npz), the oracle's hand-written backward formulas
+and the composed-torch grad-mode path."""
 import os
 
 import pytest
@@ -10,9 +8,7 @@ import torch
 
 import golden_util as gu
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PNR_TEST_BACKWARD", "0") != "1",
-                                 reason="pnr_field_backward has not been validated on a GPU yet (set PNR_TEST_BACKWARD=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def rel(a, ref):
@@ -23,7 +19,7 @@ def training_step(case, gt, fused):
     """fused: False = composed torch, 1 = field-level node (pnr_field_backward), 2 = render-level node
     (pnr_render + pnr_render_backward)."""
     import gpu_util
-    os.environ["PNR_FUSED_BACKWARD"] = str(int(fused))
+    os.environ["PNR_FUSED_BACKWARD"] = str(int(fused)) if fused != "auto" else "auto"
     net = gpu_util.build_net(case, device="cuda:0", engine="simt").train()
     net.encoder.latent = case["latent"].cuda().clone().requires_grad_(True)
     renderer = gpu_util.build_renderer(case).train()
@@ -38,7 +34,7 @@ def training_step(case, gt, fused):
     return loss.item(), net
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, "auto"])
 @pytest.mark.parametrize("name", gu.GRAD_CASE_NAMES)
 def test_fused_backward_matches_composed_torch_on_the_same_device(name, mode):
     """Same device RNG for both runs, so the samples are identical and only the backward differs."""
@@ -47,7 +43,7 @@ def test_fused_backward_matches_composed_torch_on_the_same_device(name, mode):
         l0, ref = training_step(case, g["rgb_gt"], fused=False)
         l1, net = training_step(case, g["rgb_gt"], fused=mode)
     finally:
-        os.environ["PNR_FUSED_BACKWARD"] = "0"
+        os.environ.pop("PNR_FUSED_BACKWARD", None)
     assert abs(l0 - l1) < 1e-5
     assert rel(net.encoder.latent.grad, ref.encoder.latent.grad) < 1e-3
     for (k, p), (_, q) in zip(net.mlp_coarse.named_parameters(), ref.mlp_coarse.named_parameters()):
@@ -78,8 +74,36 @@ def test_field_backward_matches_oracle_formulas(name):
         out = net(x, coarse=True, viewdirs=dirs.cuda())
         out.backward(d_out.cuda())
     finally:
-        os.environ["PNR_FUSED_BACKWARD"] = "0"
+        os.environ.pop("PNR_FUSED_BACKWARD", None)
     assert rel(x.grad.cpu(), dxyz_ref) < 1e-3
     assert rel(net.encoder.latent.grad.cpu(), dlat_ref) < 1e-3
     for k, p in net.mlp_coarse.named_parameters():
         assert rel(p.grad.cpu(), g_ref[k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", gu.GRAD_CASE_NAMES)
+def test_fused_training_step_matches_the_reference_gradients(name):
+    """The default CUDA training path (pnr_render + pnr_render_backward in one autograd node) with the fixture's draws
+    injected: loss and every gradient equal what the UNMODIFIED reference computed for train/train.py:199-215
+    (tests/golden/grad_*.npz) to <= 1e-3 relative."""
+    import gpu_util
+    from render.fused_train import fused_render_train
+    case, g = gu.load_case(name), gu.load_grad_case(name)
+    net = gpu_util.build_net(case, device="cuda:0", engine="auto").train()
+    net.encoder.latent = case["latent"].cuda().clone().requires_grad_(True)
+    renderer = gpu_util.build_renderer(case).train()
+    noise = {k: v.cuda() for k, v in case["noise"].items()}
+    out = fused_render_train(renderer, net, case["rays"].cuda(), True, noise_in=noise)
+    crit = torch.nn.MSELoss()
+    gt = g["rgb_gt"].cuda()
+    loss = crit(out.coarse.rgb, gt)
+    if case["cfg"]["n_fine"] > 0:
+        loss = loss + crit(out.fine.rgb, gt)
+    assert abs(loss.item() - g["loss"]) < 1e-5
+    loss.backward()
+    assert rel(net.encoder.latent.grad.cpu(), g["g_latent"]) < 1e-3
+    for k, p in net.mlp_coarse.named_parameters():
+        assert rel(p.grad.cpu(), g["gc"][k]) < 1e-3, ("coarse", k)
+    if net.mlp_fine is not None:
+        for k, p in net.mlp_fine.named_parameters():
+            assert rel(p.grad.cpu(), g["gf"][k]) < 1e-3, ("fine", k)

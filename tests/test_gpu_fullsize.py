@@ -86,12 +86,46 @@ def test_sharded_render_matches_single_gpu_order():
     assert torch.isfinite(rgb).all()
     # shard boundaries follow torch.chunk: replica 1 renders rays[257:]
     rep = par._replicas[1]
+    copies = rep.refreshes
+    assert copies == 3                     # coarse weights, fine weights, scene: one peer copy each
+    with torch.no_grad():
+        par(rays)
+    assert rep.refreshes == copies         # nothing changed -> nothing is re-sent (DataParallel re-broadcasts per call)
     noise = {k: v for k, v in bench.synth.draw_noise(3, n, cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"]).items()}
     with torch.no_grad():
         whole = renderer._forward_fused(net, rays, False, noise_in={k: v.cuda(0) for k, v in noise.items()}).fine.rgb
-        second = renderer._forward_fused(rep.net, rays[:, 257:].to("cuda:1"), False,
+        second = renderer._forward_fused(rep, rays[:, 257:].to("cuda:1"), False,
                                          noise_in={k: v[257:].contiguous().cuda(1) for k, v in noise.items()}).fine.rgb
     assert torch.equal(second.cpu(), whole[:, 257:].cpu())
+    # an in-place weight update (optimizer.step) and a new encode() each invalidate exactly their part
+    with torch.no_grad():
+        net.mlp_fine.lin_out.bias.add_(0.25)
+        par(rays)
+        assert rep.refreshes == copies + 2          # fine weights + scene (its P maps depend on the weights)
+        whole2 = renderer._forward_fused(net, rays, False, noise_in={k: v.cuda(0) for k, v in noise.items()}).fine.rgb
+        second2 = renderer._forward_fused(rep, rays[:, 257:].to("cuda:1"), False,
+                                          noise_in={k: v[257:].contiguous().cuda(1) for k, v in noise.items()}).fine.rgb
+    assert torch.equal(second2.cpu(), whole2[:, 257:].cpu()) and not torch.equal(whole2, whole)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4"])
+def test_oracle_parity_at_true_shapes(name):
+    """The product default (engine auto -> tensor engine) against the CPU ORACLE at the true C2 / C3 / C4 shapes (real
+    resnet34 latent: 2x512x64x64, 1x512x32x32, 3x512x150x200), 256 rays spread over a frame, injected noise --
+    the same `parity` block bench.py prints."""
+    bench, cfg, net, renderer = _scene(name, "auto")
+    rays = bench.synth.make_rays(cfg, bench.WORKLOADS[name]["frame_rays"]).cuda()[None]
+    import pnr_native as pn
+    par = bench.parity_block(net, renderer, cfg, rays, n=256)
+    assert pn.tc_status() == 0
+    assert net._fused.mlp["mlp_coarse"][3] is not None                 # the tensor engine did run
+    assert par["rays"] == 256
+    assert par["max_abs_drgb_coarse"] < 1e-4, par
+    assert par["flipped_rays"] <= 12, par                               # < 5 % of the rays
+    assert par["max_abs_drgb"] < 1e-4, par
+    assert par["psnr_db"] > 50 if par["flipped_rays"] else par["psnr_db"] > 80, par
+    lat = net.encoder.latent
+    assert lat.shape[0] * lat.shape[2] * lat.shape[3] * 512 < 2 ** 32   # 32-bit tap offsets (pnr_field_tc.cu geo[])
 
 
 @pytest.mark.parametrize("SB,NS", [(2, 2), (1, 6), (3, 1)])

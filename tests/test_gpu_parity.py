@@ -9,15 +9,17 @@ import golden_util as gu
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["simt"]
+# every golden case on the fp32 SIMT engine, and the d_hidden = 512 cases also on the tensor engine (the product
+# default: engine "auto" picks it whenever the shape allows)
+TC_CASES = ["c2_small", "c3_small", "c4_small"]
+CASE_ENGINE = [(n, "simt") for n in gu.CASE_NAMES] + [(n, "tc") for n in TC_CASES] + [(n, "auto") for n in TC_CASES]
 
 
 def _flipped_rays(z_a, z_b, tol=2e-4):
     return ((z_a - z_b).abs() > tol).any(dim=-1)
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", gu.CASE_NAMES)
+@pytest.mark.parametrize("name,engine", CASE_ENGINE)
 def test_render_parity(name, engine):
     import gpu_util
     case = gu.load_case(name)
@@ -38,8 +40,7 @@ def test_render_parity(name, engine):
         assert torch.all(f["z"][:, 1:] >= f["z"][:, :-1])  # sorted
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", gu.CASE_NAMES)
+@pytest.mark.parametrize("name,engine", CASE_ENGINE)
 def test_field_parity(name, engine):
     """PixelNeRFNet.forward on scattered points (incl. behind-camera / off-image)."""
     import gpu_util
@@ -51,7 +52,9 @@ def test_field_parity(name, engine):
         out_f = net(ref["field_xyz"].cuda(), coarse=False, viewdirs=ref["field_dirs"].cuda())
     for out, key in ((out_c, "field_coarse"), (out_f, "field_fine")):
         err = (out.cpu() - ref[key]).abs() / (1.0 + ref[key].abs())
-        assert err.max() < 5e-5, (key, err.max())
+        # fp32 engine: 5e-5 on everything; tensor engine: RGB (the contract, 1e-4 absolute) and sigma relative
+        assert err.max() < (5e-5 if engine == "simt" else 5e-4), (key, err.max())
+        assert (out.cpu()[..., :3] - ref[key][..., :3]).abs().max() < 1e-4
 
 
 def test_stage_entry_points():
@@ -93,11 +96,12 @@ def test_stage_entry_points():
     assert (zf.cpu()[~flipped] - ref["fine"]["z"][~flipped]).abs().max() < 1e-5
 
 
-def test_public_api_seeded_and_empty():
+@pytest.mark.parametrize("name,engine", [("tiny", "simt"), ("c2_small", "auto")])
+def test_public_api_seeded_and_empty(name, engine):
     """NeRFRenderer.forward / bind_parallel surface: shapes, determinism under a seed, empty shard."""
     import gpu_util
-    case = gu.load_case("tiny")
-    net = gpu_util.build_net(case, engine="simt")
+    case = gu.load_case(name)
+    net = gpu_util.build_net(case, engine=engine)
     renderer = gpu_util.build_renderer(case)
     rays = case["rays"].cuda()
     par = renderer.bind_parallel(net, [0], simple_output=True).eval()
@@ -120,17 +124,18 @@ def test_no_cpu_fallback():
         net(case["ref"]["field_xyz"], coarse=True, viewdirs=case["ref"]["field_dirs"])
 
 
+@pytest.mark.parametrize("name,engine", [("tiny", "simt"), ("c2_small", "tc")])
 @pytest.mark.parametrize("n_fine,n_fine_depth", [(6, 0), (5, 5), (0, 0)])
-def test_sample_count_edge_cases(n_fine, n_fine_depth):
+def test_sample_count_edge_cases(n_fine, n_fine_depth, name, engine):
     """No depth samples / no importance samples / coarse only (nerf.py:284-293 skips the empty sampler)."""
     import gpu_util
-    case = gu.load_case("tiny")
+    case = gu.load_case(name)
     cfg = dict(case["cfg"])
     cfg.update(n_fine=n_fine, n_fine_depth=n_fine_depth)
     case = dict(case, cfg=cfg)
     R = case["rays"].shape[0] * case["rays"].shape[1]
     case["noise"] = gu.synth.draw_noise(77, R, cfg["n_coarse"], n_fine, n_fine_depth)
-    res = gpu_util.render_case_cuda(case, engine="simt")
+    res = gpu_util.render_case_cuda(case, engine=engine)
     ref = gu.oracle_render(case)
     assert (res["coarse"]["rgb"].cpu() - ref["coarse"]["rgb"]).abs().max() < 1e-4
     if n_fine > 0:

@@ -77,3 +77,31 @@ def test_tc_matches_simt_large():
     assert (a[..., :3] - b[..., :3]).abs().max() < 1e-4
     rel = (a[..., 3] - b[..., 3]).abs() / (1.0 + b[..., 3].abs())
     assert rel.max() < 5e-4
+
+
+@pytest.mark.parametrize("variant", ["no_fine_mlp", "two_objects", "two_objects_no_fine_mlp"])
+def test_tc_variants_vs_oracle(variant):
+    """Tensor engine against the ORACLE where the reference's callers reconfigure the model: `net.mlp_fine = None`
+    (eval/eval.py:140 -> the coarse MLP serves both passes, models.py:242) and a super-batch of objects (SB = 2,
+    train/train.py:-B; here c2_small's two source views become two single-view objects with their own rays)."""
+    import gpu_util
+    case = dict(gu.load_case("c2_small"))
+    cfg = dict(case["cfg"])
+    if "no_fine_mlp" in variant:
+        case["wf"] = None
+    if "two_objects" in variant:
+        B = case["rays"].shape[1] // 2
+        case["rays"] = case["rays"][:, :2 * B].reshape(2, B, 8).contiguous()
+        case["src_poses"] = case["src_poses"].reshape(2, 1, 4, 4).contiguous()
+        case["noise"] = {k: v[:2 * B].contiguous() for k, v in case["noise"].items()}
+        cfg.update(SB=2, NS=1)
+    case["cfg"] = cfg
+    res = gpu_util.render_case_cuda(case, engine="tc")
+    _check_status()
+    ref = gu.oracle_render(case)
+    assert (res["coarse"]["rgb"].cpu() - ref["coarse"]["rgb"]).abs().max() < 1e-4
+    assert (res["coarse"]["weights"].cpu() - ref["coarse"]["weights"]).abs().max() < 1e-4
+    f, rf = res["fine"], ref["fine"]
+    flipped = ((f["z"].cpu() - rf["z"]).abs() > 2e-4).any(dim=-1)
+    assert flipped.float().mean() <= 0.07, f"{int(flipped.sum())} rays flipped a CDF bin"
+    assert (f["rgb"].cpu()[~flipped] - rf["rgb"][~flipped]).abs().max() < 1e-4
