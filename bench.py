@@ -10,8 +10,8 @@ A "step" renders one batch of synthetic rays (coarse + fine pass) of a BASELINE.
   c2 (default, the headline)  SRN-car 128x128, 2 source views, 64+32 samples   16 384 rays = one frame
   c3                          ShapeNet-NMR 64x64, 1 source view, 64+16 samples   4 096 rays = one frame
   c4                          DTU 400x300, 3 source views, 96+48 samples       120 000 rays = one frame
-all with ResnetFC d=512 x 5 blocks, random-init weights with re-randomised fc_1, and a real resnet34 trunk for the
-latent.  `value` = rays/s of the whole job with inputs resident in HBM; `e2e` = the same through the public API
+all with ResnetFC d=512 x 5 blocks, random-init weights with re-randomised fc_1 (synth.bench_mlp_weights: lin_z scaled
+so the random network renders a non-blank, semi-transparent volume), and a real resnet34 trunk for the latent.  `value` = rays/s of the whole job with inputs resident in HBM; `e2e` = the same through the public API
 (`NeRFRenderer.bind_parallel(net)(rays)`) from pinned HOST rays to HOST pixels.
 
 Ranks shard rays (render/sharding.py, torch.chunk order): `--scaling weak` (default) gives every GPU one frame,
@@ -172,8 +172,8 @@ def build_scene(cfg, device, engine):
     conf = model_conf(cfg)
     torch.manual_seed(0)
     net = make_model(conf["model"])
-    net.mlp_coarse.load_state_dict(synth.make_mlp_weights(11, cfg["d_hidden"]))
-    net.mlp_fine.load_state_dict(synth.make_mlp_weights(12, cfg["d_hidden"]))
+    net.mlp_coarse.load_state_dict(synth.bench_mlp_weights(11, cfg["d_hidden"]))
+    net.mlp_fine.load_state_dict(synth.bench_mlp_weights(12, cfg["d_hidden"]))
     net = net.to(device).eval()
     net.engine = engine
     renderer = NeRFRenderer.from_conf(conf["renderer"], eval_batch_size=50000).to(device).eval()
@@ -361,6 +361,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["text"], "rays_per_step": total, "rays_per_step_per_gpu": n_mine,
                        "engine": args.engine, "l2_flush_between_steps": True,
+                       "weights": f"synthetic kaiming (synth.bench_mlp_weights, lin_z x{synth.BENCH_LATENT_GAIN}), "
+                                  "random-init resnet34 trunk",
                        "parallelism": f"ray-sharded x{world} ({args.scaling})", "flop_per_ray": fl},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": total * 8 * 4,
                     "d2h_bytes_per_step": total * 4 * 4},
@@ -407,8 +409,8 @@ def build_reference_scene(workload, device):
     rh = _load("pnr_ref_harness", os.path.join(ROOT, "oracle", "ref_harness.py"))
     cfg = synth.CONFIGS[workload]
     torch.manual_seed(0)
-    net, renderer = rh.build_reference(cfg["d_hidden"], synth.make_mlp_weights(11, cfg["d_hidden"]),
-                                       synth.make_mlp_weights(12, cfg["d_hidden"]), cfg["n_coarse"], cfg["n_fine"],
+    net, renderer = rh.build_reference(cfg["d_hidden"], synth.bench_mlp_weights(11, cfg["d_hidden"]),
+                                       synth.bench_mlp_weights(12, cfg["d_hidden"]), cfg["n_coarse"], cfg["n_fine"],
                                        cfg["n_fine_depth"], white_bkgd=cfg["white_bkgd"], eval_batch_size=50000,
                                        use_first_pool=cfg["use_first_pool"])
     net = net.to(device).eval()
@@ -458,7 +460,7 @@ def cpu_arm(workload):
         src, _, focal, c = synth.make_cameras(cfg)
         latent = synth.make_latent(5, cfg["NS"], cfg["H"] // 2, cfg["W"] // 2)
         state = oracle.encode_state(src, focal, c[None], cfg["W"], cfg["H"])
-        wc, wf = synth.make_mlp_weights(11, cfg["d_hidden"]), synth.make_mlp_weights(12, cfg["d_hidden"])
+        wc, wf = synth.bench_mlp_weights(11, cfg["d_hidden"]), synth.bench_mlp_weights(12, cfg["d_hidden"])
 
         def render(rays):
             noise = synth.draw_noise(3, rays.shape[1], cfg["n_coarse"], cfg["n_fine"], cfg["n_fine_depth"])

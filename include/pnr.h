@@ -168,8 +168,8 @@ int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, c
  *   grad          : a PnrMlp whose weight pointers are WRITABLE gradient buffers of the same shapes; accumulated (+=)
  *   d_latent_nhwc : [V][Hl][Wl][C] channels-last gradient of the latent; accumulated (+=); may be NULL
  *   d_xyz         : [SB][P][3] gradient of the sample positions (overwritten); may be NULL
- * fp32 SIMT recompute-in-backward (first path; arithmetic = oracle/pnr_backward.py).  Verified on the host emulator
- * (tests/cuda_emu), not yet run on a GPU: nothing in the default product path calls it. */
+ * Recompute-in-backward (arithmetic = oracle/pnr_backward.py); the GEMMs run on the tensor cores (split-bf16 tcgen05,
+ * PNR_BWD_GEMM=simt selects the fp32 FFMA SGEMM).  This is what PixelNeRFNet.forward's autograd node calls on CUDA. */
 size_t pnr_field_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P);
 int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, const float* viewdirs,
                        const float* d_out, const PnrMlp* grad, float* d_latent_nhwc, float* d_xyz, int64_t P,
@@ -183,8 +183,8 @@ int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xy
  *   d_latent_nhwc: [V][Hl][Wl][C], accumulated (+=); may be NULL
  * The coarse weights are detached for importance sampling but the coarse depth is not (nerf.py:286-291), so the fine
  * loss also reaches the coarse MLP.  Gradients w.r.t. the depth / weights outputs are not supported.
- * fp32 SIMT; arithmetic = oracle/pnr_backward.py::train_loss_backward.  Verified on the host emulator
- * (tests/cuda_emu) against the reference's own gradients; not yet run on a GPU. */
+ * Arithmetic = oracle/pnr_backward.py::train_loss_backward; validated on B200 against the reference's own gradients.
+ * This is the backward of the default CUDA training path (NeRFRenderer.forward in grad mode). */
 size_t pnr_render_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coarse,
                                            const PnrMlp* mlp_fine, const PnrRenderCfg* cfg, int64_t B);
 int pnr_render_backward(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine,
@@ -213,6 +213,13 @@ int pnr_pack_mlp(const PnrMlp* mlp, void* packed, size_t packed_bytes, void* str
 size_t pnr_project_latent_bytes(const PnrScene* scene, const PnrMlp* mlp);
 int pnr_project_latent(const PnrScene* scene, const PnrMlp* mlp, float* proj, size_t proj_bytes,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook for the dense contraction the backward path is built from (nn.Linear forward / input gradient / weight
+ * gradient are all this "NT" product): C[M][N] (+)= act(A[M][lda]) * W[N][K]^T (+ bias[N]), fp32 in and out.
+ * engine = PNR_ENGINE_SIMT: fp32 FFMA SGEMM; PNR_ENGINE_TC (or AUTO): split-bf16 tcgen05 GEMM (3 products, fp32
+ * accumulate, split-K with atomics when the output has few tiles).  K % 16 == 0, rows 16-byte aligned. */
+int pnr_gemm_nt(const float* A, int32_t lda, const float* W, const float* bias, float* C, int32_t ldc, int32_t M,
+                int32_t N, int32_t K, int32_t relu_a, int32_t accum, int32_t engine, void* stream);
 
 /* How many kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t pnr_launch_count(void);

@@ -22,6 +22,11 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
+          bool relu_a, bool accum, cudaStream_t s);                 // pnr_field_simt.cu
+int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                int K, bool relu_a, bool accum, cudaStream_t s);    // pnr_gemm_tc.cu
+
 // ---- dominant-kernel profiling ----------------------------------------------------------
 static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_ev;  // pairs (start, stop)
@@ -213,6 +218,16 @@ int pnr_field_eval(const PnrScene* scene, const PnrMlp* mlp, const float* xyz, c
   src.K = 1;
   return field_dispatch(*scene, *mlp, scene->proj_coarse, src, P * scene->SB, out, engine, workspace,
                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int pnr_gemm_nt(const float* A, int32_t lda, const float* W, const float* bias, float* C, int32_t ldc, int32_t M,
+                int32_t N, int32_t K, int32_t relu_a, int32_t accum, int32_t engine, void* stream) {
+  PNR_CHECK_ARG(M >= 0 && N >= 0 && K >= 16 && K % 16 == 0, "bad sizes (K must be a positive multiple of 16)");
+  if (M == 0 || N == 0) return PNR_OK;
+  PNR_CHECK_ARG(A && W && C, "NULL pointer");
+  PNR_CHECK_ARG(lda >= K && ldc >= N && lda % 4 == 0, "bad leading dimensions");
+  if (engine == PNR_ENGINE_SIMT) return sgemm(A, lda, W, bias, C, ldc, M, N, K, relu_a != 0, accum != 0, (cudaStream_t)stream);
+  return gemm_bf16x3(A, lda, W, K, bias, C, ldc, M, N, K, relu_a != 0, accum != 0, (cudaStream_t)stream);
 }
 
 size_t pnr_field_backward_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp, int64_t P) {

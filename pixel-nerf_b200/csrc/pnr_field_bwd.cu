@@ -9,9 +9,10 @@
 // followed by one warp per point for pos-enc, projection and the 4-tap gather (latent scatter + d uv).
 // Row order inside a chunk is the forward SIMT engine's: row = local_point * NS + view.
 //
-// STATUS: compiles for sm_100a and is exported through the C ABI, but has NOT yet been run on a GPU (the round's GPU
-// budget was spent before it was written).  Nothing in the default product path calls it; tests/test_gpu_backward.py
-// is skipped unless PNR_TEST_BACKWARD=1.
+// The GEMMs run on the tensor cores by default (split-bf16 tcgen05 GEMM, pnr_gemm_tc.cu); PNR_BWD_GEMM=simt selects
+// the fp32 FFMA SGEMM instead (the first, reference implementation of this path).
+// Validated on B200 against the oracle's formulas, the composed-torch path and the reference's own gradients
+// (tests/test_gpu_backward.py), compute-sanitizer memcheck clean.
 #include <stdlib.h>
 
 #include "pnr_geom.cuh"
@@ -20,12 +21,29 @@ namespace pnr {
 
 int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
           bool relu_a, bool accum, cudaStream_t s);
+int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                int K, bool relu_a, bool accum, cudaStream_t s);   // pnr_gemm_tc.cu
 __global__ void k_pad_rows(const float* __restrict__ src, float* __restrict__ dst, int rows, int k_src, int k_dst);
 __global__ void k_view_mean(const float* __restrict__ X, float* __restrict__ Y, int64_t n_pts, int NS, int d);
 
 namespace bwd {
 
 static inline int pad16(int x) { return (x + 15) / 16 * 16; }
+
+// C (+)= act(A) W^T + bias on the tensor cores (default) or the fp32 SIMT SGEMM (PNR_BWD_GEMM=simt)
+static bool use_tc_gemm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PNR_BWD_GEMM");
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v == 1;
+}
+static int gemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
+                bool relu_a, bool accum, cudaStream_t s) {
+  if (use_tc_gemm()) return gemm_bf16x3(A, lda, W, K, bias, C, ldc, M, N, K, relu_a, accum, s);
+  return sgemm(A, lda, W, bias, C, ldc, M, N, K, relu_a, accum, s);
+}
 
 // dst[c][m] = f(src[m][c]) for m < M (f = identity or ReLU), 0 for M <= m < Mpad.   32x32 tiles.
 template <bool RELU>
@@ -341,7 +359,7 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
     };
     float* cur = dst_of(0);
     int rows_cur = R;
-    BW(sgemm(b.feat, 48, b.w_in, mlp.lin_in_b, cur, d, R, d, 48, false, false, s));
+    BW(gemm(b.feat, 48, b.w_in, mlp.lin_in_b, cur, d, R, d, 48, false, false, s));
     for (int blk = 0; blk < nb; ++blk) {
       if (blk == comb && comb < nb) {
         if (NS > 1) {
@@ -351,11 +369,11 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
         }
         rows_cur = (int)n;
       }
-      if (blk < comb) BW(sgemm(b.lat, L, mlp.lin_z_w[blk], mlp.lin_z_b[blk], cur, d, rows_cur, d, L, false, true, s));
-      BW(sgemm(cur, d, mlp.fc0_w[blk], mlp.fc0_b[blk], b.nbuf[blk], d, rows_cur, d, d, true, false, s));
+      if (blk < comb) BW(gemm(b.lat, L, mlp.lin_z_w[blk], mlp.lin_z_b[blk], cur, d, rows_cur, d, L, false, true, s));
+      BW(gemm(cur, d, mlp.fc0_w[blk], mlp.fc0_b[blk], b.nbuf[blk], d, rows_cur, d, d, true, false, s));
       float* nxt = dst_of(blk + 1);
       PNR_CUDA(cudaMemcpyAsync(nxt, cur, (size_t)rows_cur * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      BW(sgemm(b.nbuf[blk], d, mlp.fc1_w[blk], mlp.fc1_b[blk], nxt, d, rows_cur, d, d, true, true, s));
+      BW(gemm(b.nbuf[blk], d, mlp.fc1_w[blk], mlp.fc1_b[blk], nxt, d, rows_cur, d, d, true, true, s));
       cur = nxt;
     }
     // ---------------- backward ----------------
@@ -365,7 +383,7 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
     PNR_LAUNCH_CHECK();
     BW(transpose_pad<false>(b.do4, 4, rows_last, 4, b.tA, rlp, s));
     BW(transpose_pad<true>(b.hlast, d, rows_last, d, b.tB, rlp, s));
-    BW(sgemm(b.tA, rlp, b.tB, nullptr, const_cast<float*>(grad.lin_out_w), d, 4, d, rlp, false, true, s));
+    BW(gemm(b.tA, rlp, b.tB, nullptr, const_cast<float*>(grad.lin_out_w), d, 4, d, rlp, false, true, s));
     BW(rowsum_acc(b.tA, rlp, 4, const_cast<float*>(grad.lin_out_b), s));
     PNR_CUDA(cudaMemsetAsync(b.dlat, 0, (size_t)R * L * sizeof(float), s));
     bool lat_transposed = false;
@@ -379,17 +397,17 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
       // fc_1: dW1 += dh^T relu(n), db1 += colsum(dh); dn = (dh W1) * (n > 0)
       BW(transpose_pad<false>(dh, d, rows_b, d, b.tA, Mp, s));
       BW(transpose_pad<true>(b.nbuf[blk], d, rows_b, d, b.tB, Mp, s));
-      BW(sgemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc1_w[blk]), d, d, d, Mp, false, true, s));
+      BW(gemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc1_w[blk]), d, d, d, Mp, false, true, s));
       BW(rowsum_acc(b.tA, Mp, d, const_cast<float*>(grad.fc1_b[blk]), s));
-      BW(sgemm(dh, d, b.w1T[blk], nullptr, b.T, d, rows_b, d, d, false, false, s));
+      BW(gemm(dh, d, b.w1T[blk], nullptr, b.T, d, rows_b, d, d, false, false, s));
       k_mask<<<eg, 256, 0, s>>>(b.T, b.nbuf[blk], cnt);
       PNR_LAUNCH_CHECK();
       // fc_0: dW0 += dn^T relu(hpre), db0 += colsum(dn); dh += (dn W0) * (hpre > 0)
       BW(transpose_pad<false>(b.T, d, rows_b, d, b.tA, Mp, s));
       BW(transpose_pad<true>(b.hpre[blk], d, rows_b, d, b.tB, Mp, s));
-      BW(sgemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc0_w[blk]), d, d, d, Mp, false, true, s));
+      BW(gemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc0_w[blk]), d, d, d, Mp, false, true, s));
       BW(rowsum_acc(b.tA, Mp, d, const_cast<float*>(grad.fc0_b[blk]), s));
-      BW(sgemm(b.T, d, b.w0T[blk], nullptr, b.T2, d, rows_b, d, d, false, false, s));
+      BW(gemm(b.T, d, b.w0T[blk], nullptr, b.T2, d, rows_b, d, d, false, false, s));
       k_mask_add<<<eg, 256, 0, s>>>(dh, b.T2, b.hpre[blk], cnt);
       PNR_LAUNCH_CHECK();
       if (blk < comb) {   // x = x + lin_z[blk](latent): dWz += dh^T lat, dbz += colsum(dh), dlat += dh Wz
@@ -398,9 +416,9 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
           lat_transposed = true;
         }
         BW(transpose_pad<false>(dh, d, R, d, b.tA, Rp, s));
-        BW(sgemm(b.tA, Rp, b.latT, nullptr, const_cast<float*>(grad.lin_z_w[blk]), L, d, L, Rp, false, true, s));
+        BW(gemm(b.tA, Rp, b.latT, nullptr, const_cast<float*>(grad.lin_z_w[blk]), L, d, L, Rp, false, true, s));
         BW(rowsum_acc(b.tA, Rp, d, const_cast<float*>(grad.lin_z_b[blk]), s));
-        BW(sgemm(dh, d, b.wzT[blk], nullptr, b.dlat, L, R, L, d, false, true, s));
+        BW(gemm(dh, d, b.wzT[blk], nullptr, b.dlat, L, R, L, d, false, true, s));
       }
       if (blk == comb && comb < nb && NS > 1) {   // the block's input was the mean over views
         k_view_mean_bwd<<<(unsigned)(((int64_t)R * d + 255) / 256), 256, 0, s>>>(dh, dh_other, n, NS, d);
@@ -411,11 +429,11 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
     // lin_in: dW += dh^T feat (42 of the 48 padded columns), db += colsum(dh), dfeat = dh W_in
     BW(transpose_pad<false>(dh, d, R, d, b.tA, Rp, s));
     BW(transpose_pad<false>(b.feat, 48, R, 48, b.featT, Rp, s));
-    BW(sgemm(b.tA, Rp, b.featT, nullptr, b.tmp_win, 48, d, 48, Rp, false, false, s));
+    BW(gemm(b.tA, Rp, b.featT, nullptr, b.tmp_win, 48, d, 48, Rp, false, false, s));
     k_add_cols<<<(d * mlp.d_in + 255) / 256, 256, 0, s>>>(const_cast<float*>(grad.lin_in_w), b.tmp_win, d, mlp.d_in, 48);
     PNR_LAUNCH_CHECK();
     BW(rowsum_acc(b.tA, Rp, d, const_cast<float*>(grad.lin_in_b), s));
-    BW(sgemm(dh, d, b.w_inT, nullptr, b.dfeat, 48, R, 48, d, false, false, s));
+    BW(gemm(dh, d, b.w_inT, nullptr, b.dfeat, 48, R, 48, d, false, false, s));
     k_geom_bwd<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(sc, src, g0, n, b.dfeat, b.dlat, d_latent, d_xyz);
     PNR_LAUNCH_CHECK();
   }

@@ -754,6 +754,8 @@ static int get_status_buffer(int** out) {
 
 }  // namespace tc
 
+int tc_status_buffer(int** out) { return tc::get_status_buffer(out); }   // shared with pnr_gemm_tc.cu
+
 bool tc_supported(const PnrScene& sc, const PnrMlp& m) {
   // the kernel addresses the projected maps with 32-bit ELEMENT offsets (geo[0..3]): one map must stay below 2^32 floats
   const unsigned long long map_elems = (unsigned long long)sc.SB * sc.NS * sc.Hl * sc.Wl * tc::D;

@@ -10,7 +10,7 @@ import os
 
 import torch
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
+_HERE = os.path.dirname(os.path.realpath(__file__))   # realpath: `src/` may be reached through an overlay symlink
 LIB_PATH = os.environ.get("PNR_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libpnr_sm100.so"))
 
 PNR_MAX_BLOCKS = 8
@@ -92,6 +92,8 @@ def declare(L):
     L.pnr_project_latent_bytes.argtypes = [P(PnrScene), P(PnrMlp)]
     L.pnr_project_latent_bytes.restype = sz
     L.pnr_project_latent.argtypes = [P(PnrScene), P(PnrMlp), vp, sz, vp, sz, vp]
+    L.pnr_gemm_nt.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.pnr_gemm_nt.restype = C.c_int
     L.pnr_profile_begin.restype = C.c_int
     L.pnr_tc_status.argtypes = [P(C.c_int)]
     L.pnr_tc_status.restype = C.c_int

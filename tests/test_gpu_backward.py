@@ -107,3 +107,32 @@ def test_fused_training_step_matches_the_reference_gradients(name):
     if net.mlp_fine is not None:
         for k, p in net.mlp_fine.named_parameters():
             assert rel(p.grad.cpu(), g["gf"][k]) < 1e-3, ("fine", k)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K,relu,accum", [(300, 512, 512, True, False),     # forward layer, ragged M
+                                               (512, 512, 4000, False, True),    # weight gradient: K = rows, split-K
+                                               (4, 512, 1008, False, True),      # lin_out weight gradient
+                                               (1000, 48, 512, False, False),    # d_feat = dh W_in
+                                               (777, 130, 48, False, True)])     # ragged N, one k-step
+def test_gemm_nt_engines(M, N, K, relu, accum, engine):
+    """pnr_gemm_nt (the contraction of the backward path) against a float64 product: the fp32 FFMA engine to fp32
+    rounding, the split-bf16 tcgen05 engine to 16-bit-mantissa operands (<= 3e-5 of the row/column scale)."""
+    import gpu_util  # noqa: F401
+    import pnr_native as pn
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 3e-4).to(dev)          # gradient-sized values: no scaling may be needed
+    W = torch.randn(N, K, generator=g).to(dev)
+    b = torch.randn(N, generator=g).to(dev) * 1e-3
+    C0 = torch.randn(M, N + 8, generator=g).to(dev) * 1e-3       # ldc > N: the pad columns must stay untouched
+    C = C0.clone()
+    pn.check(pn.lib().pnr_gemm_nt(pn.dptr(A), K, pn.dptr(W), pn.dptr(b), pn.dptr(C), N + 8, M, N, K, int(relu), int(accum),
+                                  pn.ENGINES[engine], pn.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    Ad = torch.relu(A.double()) if relu else A.double()
+    ref = Ad @ W.double().t() + b.double() + (C0[:, :N].double() if accum else 0.0)
+    scale = (Ad.abs() @ W.double().abs().t()).max()
+    err = (C[:, :N].double() - ref).abs().max() / scale
+    assert err < (2e-6 if engine == "simt" else 3e-5), err
+    assert torch.equal(C[:, N:], C0[:, N:])
