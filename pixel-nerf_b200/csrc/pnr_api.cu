@@ -3,6 +3,7 @@
 // (src/render/nerf.py:251-303).  No CPU fallback: everything below launches CUDA kernels.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -363,7 +364,21 @@ size_t pnr_render_workspace_bytes(const PnrScene* scene, const PnrMlp* mlp_coars
     size_t f2 = field_ws(*scene, *mlp_fine, R * K, cfg->engine);
     if (f2 > f) f = f2;
   }
+  if (cfg->engine != PNR_ENGINE_SIMT && tc_supported(*scene, *mlp_coarse)) {
+    size_t f3 = tc_render_workspace_bytes(*scene, R, cfg->n_coarse, cfg->n_fine);
+    if (f3 > f) f = f3;
+  }
   return b + f + 4096;
+}
+
+// PNR_RENDER_FUSED=0 keeps the tensor engine on the stage-by-stage orchestration (six launches); default: one launch.
+static bool fused_render_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PNR_RENDER_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int pnr_render(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* mlp_fine, const PnrRenderCfg* cfg,
@@ -400,6 +415,21 @@ int pnr_render(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* ml
   char* rest = ar.base + align_up(ar.off, 256);
   size_t rest_bytes = workspace_bytes - align_up(ar.off, 256);
 
+  if (Kf - Kfd > 0) PNR_CHECK_ARG(noise->u_fine && noise->u_fine_jit, "u_fine / u_fine_jit is NULL");
+  if (Kf > 0 && Kfd > 0) PNR_CHECK_ARG(noise->n_depth, "n_depth is NULL");
+  {
+    // ---- tensor engine: the whole call is ONE launch (sampling, both field passes, compositing, resampling) ----
+    const PnrMlp* mf = mlp_fine ? mlp_fine : mlp_coarse;                       // models.py:242
+    const float* pf = mlp_fine ? scene->proj_fine : scene->proj_coarse;
+    int ec = resolve_engine(*scene, *mlp_coarse, scene->proj_coarse, cfg->engine);
+    if (ec < 0) return ec;
+    int ef = Kf > 0 ? resolve_engine(*scene, *mf, pf, cfg->engine) : ec;
+    if (ef < 0) return ef;
+    if (ec == PNR_ENGINE_TC && ef == PNR_ENGINE_TC && fused_render_enabled())
+      return tc_render(*scene, *mlp_coarse, *mf, scene->proj_coarse, pf, *cfg, rays, *noise, zc, wc, zf, *out, B, rest,
+                       rest_bytes, s);
+  }
+
   // ---- coarse pass (nerf.py:273-276) ----
   if ((rc = launch_sample_coarse(rays, noise->lin_steps, noise->u_coarse, zc, R, Kc, s))) return rc;
   PointSource src{};
@@ -416,8 +446,6 @@ int pnr_render(const PnrScene* scene, const PnrMlp* mlp_coarse, const PnrMlp* ml
   if (Kf == 0) return PNR_OK;
 
   // ---- fine pass (nerf.py:284-301) ----
-  if (Kf - Kfd > 0) PNR_CHECK_ARG(noise->u_fine && noise->u_fine_jit, "u_fine / u_fine_jit is NULL");
-  if (Kfd > 0) PNR_CHECK_ARG(noise->n_depth, "n_depth is NULL");
   if ((rc = launch_sample_fine(rays, zc, wc, out->depth_coarse, noise->u_fine, noise->u_fine_jit, noise->n_depth,
                                cfg->depth_std, zf, R, Kc, Kf, Kfd, s)))
     return rc;

@@ -117,5 +117,11 @@ bool tc_supported(const PnrScene& sc, const PnrMlp& mlp);
 size_t tc_workspace_bytes(const PnrScene& sc, const PnrMlp& mlp, int64_t total_points);
 int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
                   int64_t total_points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+// NeRFRenderer.forward in one launch (coarse + fine field passes with compositing / resampling in the ray-completion
+// epilogue); zc, wc [R][Kc] and zf [R][Kc+Kf] are caller or workspace buffers that also serve as outputs.
+size_t tc_render_workspace_bytes(const PnrScene& sc, int64_t R, int Kc, int Kf);
+int tc_render(const PnrScene& sc, const PnrMlp& mlp_coarse, const PnrMlp& mlp_fine, const float* proj_coarse,
+              const float* proj_fine, const PnrRenderCfg& cfg, const float* rays, const PnrNoise& noise, float* zc,
+              float* wc, float* zf, const PnrRenderOut& out, int64_t B, void* ws, size_t ws_bytes, cudaStream_t s);
 
 }  // namespace pnr

@@ -25,6 +25,7 @@
 
 #include "pnr_common.cuh"
 #include "pnr_geom.cuh"
+#include "pnr_ray_ops.cuh"
 #include "pnr_tc_ptx.cuh"
 
 namespace pnr {
@@ -69,18 +70,49 @@ constexpr int BAR_F_FULL = BAR_A_FREE + 8;
 constexpr int BAR_ACC = BAR_F_FULL + 1;             // [2] accumulator block 0 / block 1 ready
 constexpr int BAR_COUNT = BAR_ACC + 2;
 constexpr int SM_TMEM_PTR = SM_BAR + BAR_COUNT * 8;
+constexpr int SM_NLIST = SM_TMEM_PTR + 8;     // fused render: number of rays this CTA completed in the current pass
+constexpr int FLUSH_SCRATCH_BYTES = A_BYTES / NWORKER_WARPS;   // per-warp scratch (cdf + merged samples) in the idle A buffer
 
+
+// One evaluation pass of the field: the coarse or the fine MLP over a set of points.
+struct Pass {
+  const uint8_t* packed;   // tensor-engine weight image of this pass's MLP (pnr_pack_mlp)
+  const float* proj;       // [3][V][Hl][Wl][512] projected maps of this pass's MLP
+  const float* fc0_b[5];
+  const float* fc1_b[5];
+  const float* lin_out_w;
+  const float* lin_out_b;
+  float* out;              // [total_points][4]
+  int64_t total_points;
+  int64_t n_tiles;
+  int64_t P;               // points per object (sb = point / P)
+  int K;                   // samples per ray (fused render)
+};
+
+// Fused render (NeRFRenderer.forward in ONE launch, src/render/nerf.py:251-303): pass 0 = coarse, pass 1 = fine.  The
+// CTA that stores the last field value of a ray finishes the ray: compositing (+ importance / depth resampling and the
+// sorted merge after the coarse pass) happens in that CTA at the end of its pass ("flush"), fine tiles wait for the
+// `ready` flag of their rays.  rays == NULL: plain field evaluation (PixelNeRFNet.forward), one pass.
+struct Render {
+  const float* rays;       // [R][8]
+  const float *lin, *u_c, *u_f, *u_j, *n_d;
+  float *zc, *wc, *zf;     // [R][Kc], [R][Kc], [R][Kc+Kf]
+  float *rgb_c, *depth_c, *rgb_f, *depth_f, *w_f;
+  int* count;              // [2][R] field values stored so far per ray and pass
+  int* ready;              // [R] 1 = the ray's fine samples are written
+  int* lists;              // [gridDim.x][cap] rays completed by a CTA in the current pass
+  int64_t R;
+  int cap, Kc, Kf, Kfd, white;
+  float depth_std;
+};
 
 struct Params {
   PnrScene sc;
-  PointSource src;
-  PnrMlp mlp;
-  const uint8_t* packed;
-  const float* proj;      // [3][V][Hl][Wl][512]
+  PointSource src;        // plain field evaluation only
+  Pass pass[2];
+  Render rn;
   float* scratch;         // [gridDim.x][512][64]
-  float* out;             // [total_points][4]
-  int64_t total_points;
-  int64_t n_tiles;
+  int npass;
   int* status;
 };
 
@@ -218,7 +250,7 @@ __device__ __forceinline__ void stage_gather_pair(uint8_t* smem, uint32_t smem_u
 // TMEM loads and bias loads of the next step are issued before the current step is processed; MODE_GATHER reads the
 // staged gather values back from shared memory (staged here as the chunks are released, when gated).
 template <int MODE>
-__device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, uint32_t acc_col,
+__device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, const float* __restrict__ lin_out_w, uint32_t acc_col,
                                          const float* __restrict__ bias, const float* __restrict__ proj_i,
                                          int view, float* __restrict__ scratch, float* out_part, uint32_t acc_phase,
                                          bool gate, uint32_t free_par, int warp, int tag) {
@@ -316,7 +348,7 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
         tmem_st8(c.tmem + X_COL + col, z);
       }
       if (MODE == MODE_OUT) {
-        const float* W = p.mlp.lin_out_w + n0;
+        const float* W = lin_out_w + n0;
 #pragma unroll
         for (int e4 = 0; e4 < 2; ++e4) {
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + 0 * D) + e4);
@@ -354,6 +386,44 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, ui
   }
 }
 
+// Loads of values that OTHER CTAs wrote during this launch (field values, samples): L2, never a stale L1 line.
+struct LdCg {
+  __device__ __forceinline__ float operator()(const float* q) const { return __ldcg(q); }
+};
+struct LdCg4 {
+  __device__ __forceinline__ float4 operator()(const float4* q) const { return __ldcg(q); }
+};
+
+// Fused render: finish ray `ray` of pass `ps` (one warp).  Coarse pass: compositing (nerf.py:222-249), then importance
+// + depth-centred resampling and the sorted merge (nerf.py:120-161, 285-295) into zf, then the ray's `ready` flag.
+// Fine pass: compositing into the fine outputs.
+__device__ __forceinline__ void finish_ray(const Params& p, int ps, int64_t ray, float* scratch, int lane) {
+  const Render& rn = p.rn;
+  const float* rr = rn.rays + ray * 8;
+  const float near = rr[6], far = rr[7];
+  const int Kc = rn.Kc, K = rn.Kc + rn.Kf;
+  if (ps == 0) {
+    if (lane == 0)
+      composite_ray(rn.zc + ray * Kc, reinterpret_cast<const float4*>(p.pass[0].out) + ray * Kc, far, Kc, rn.white,
+                    rn.wc + ray * Kc, rn.rgb_c + ray * 3, rn.depth_c + ray, LdCg(), LdCg4());
+    __syncwarp();
+    if (p.npass > 1) {
+      const int Ku = rn.Kf - rn.Kfd;
+      sample_fine_ray(near, far, rn.zc + ray * Kc, rn.wc + ray * Kc, rn.Kfd > 0 ? __ldcg(rn.depth_c + ray) : 0.f,
+                      rn.u_f + ray * Ku, rn.u_j + ray * Ku, rn.n_d + ray * rn.Kfd, rn.depth_std, rn.zf + ray * K, Kc,
+                      rn.Kf, rn.Kfd, scratch, lane, LdCg());
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(rn.ready + ray) = 1;
+    }
+  } else {
+    if (lane == 0)
+      composite_ray(rn.zf + ray * K, reinterpret_cast<const float4*>(p.pass[1].out) + ray * K, far, K, rn.white,
+                    rn.w_f ? rn.w_f + ray * K : nullptr, rn.rgb_f + ray * 3, rn.depth_f + ray, LdCg(), LdCg4());
+    __syncwarp();
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field_tc(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,7 +432,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
   const int n_pairs = gridDim.x >> 1;
   const uint32_t bar_base = smem_u32(smem + SM_BAR);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM_TMEM_PTR);
+  int* n_list = reinterpret_cast<int*>(smem + SM_NLIST);
   const int NS = p.sc.NS;
+  const bool render = p.rn.rays != nullptr;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
@@ -377,6 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     mbar_init(bar_base + BAR_F_FULL * 8, 2 * NWORKER_WARPS);
     mbar_init(bar_base + (BAR_ACC + 0) * 8, 1);
     mbar_init(bar_base + (BAR_ACC + 1) * 8, 1);
+    *n_list = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -390,10 +463,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const float w_scale = reinterpret_cast<const float*>(p.packed)[0];
-  const float w_inv = reinterpret_cast<const float*>(p.packed)[1];
-  const uint8_t* slots = p.packed + HEADER_BYTES + (size_t)rank * SLOTS_PER_RANK * SLOT_BYTES;
   const size_t map_stride = (size_t)p.sc.SB * NS * p.sc.Hl * p.sc.Wl * D;
 
   if (warp < NWORKER_WARPS) {
@@ -408,11 +477,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.n_hi = q >> 1;                 // which 128 features of a 256-wide MMA block live in these lanes
     c.tmem = tmem_base + ((uint32_t)(32 * q) << 16);
     c.bar_base = bar_base;
-    c.w_scale = w_scale;
-    c.w_inv = w_inv;
-    long long t_acc = 0, t_geo = 0;
+    long long t_acc = 0;
     c.t_acc = &t_acc;
-    const long long t_wstart = clock64();
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
     float* out_part = reinterpret_cast<float*>(smem + SM_PART);
     uint32_t acc_phase = 0;
@@ -420,109 +486,177 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     const int grow = threadIdx.x & 63;   // row handled in the geometry stage
     const int gsub = threadIdx.x >> 6;   // 0..7: which 6 of the 48 input channels
 
-    for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-      int64_t pt = tile * TILE_POINTS + rank * ROWS + grow;
-      if (pt >= p.total_points) pt = p.total_points - 1;
-      const int sb = (int)(pt / p.src.P);
-      float x[3], d[3];
-      load_point(p.src, pt, x, d);
-      for (int v = 0; v < NS; ++v) {
-        // ---- geometry + the 42 input channels -> A chunk 0 (lin_in operand) ----
-        {
-          const long long tg0 = clock64();
-          PointGeom pg = point_geometry(p.sc, sb, v, x, d);
-          if (gsub == 0) {
-            uint32_t* geo = reinterpret_cast<uint32_t*>(smem + SM_GEO) + grow * 8;
-            const uint32_t vbase = (uint32_t)(sb * NS + v) * p.sc.Hl * p.sc.Wl;
-            geo[0] = (vbase + pg.y0 * p.sc.Wl + pg.x0) * D;
-            geo[1] = (vbase + pg.y0 * p.sc.Wl + pg.x1) * D;
-            geo[2] = (vbase + pg.y1 * p.sc.Wl + pg.x0) * D;
-            geo[3] = (vbase + pg.y1 * p.sc.Wl + pg.x1) * D;
-            geo[4] = __float_as_uint(pg.w_nw);
-            geo[5] = __float_as_uint(pg.w_ne);
-            geo[6] = __float_as_uint(pg.w_sw);
-            geo[7] = __float_as_uint(pg.w_se);
+    for (int ps = 0; ps < p.npass; ++ps) {
+      const Pass& P = p.pass[ps];
+      c.w_scale = reinterpret_cast<const float*>(P.packed)[0];
+      c.w_inv = reinterpret_cast<const float*>(P.packed)[1];
+      for (int64_t tile = pair; tile < P.n_tiles; tile += n_pairs) {
+        const int64_t pt_raw = tile * TILE_POINTS + rank * ROWS + grow;
+        const int64_t pt = pt_raw < P.total_points ? pt_raw : P.total_points - 1;
+        const int sb = (int)(pt / P.P);
+        float x[3], d[3];
+        if (render) {
+          // the sample depth is produced here: stratified draw (coarse, nerf.py:98-113) or the merged fine sample that
+          // the CTA which finished the ray's coarse pass has written
+          const int64_t ray = pt / P.K;
+          const int k = (int)(pt - ray * P.K);
+          const float* rr = p.rn.rays + ray * 8;
+          float zz;
+          if (ps == 0) {
+            zz = coarse_sample(rr[6], rr[7], p.rn.lin ? p.rn.lin[k] : lin_step_value(k, P.K), p.rn.u_c[pt], P.K);
+            if (gsub == 0 && pt_raw < P.total_points) p.rn.zc[pt] = zz;
+          } else {
+            const volatile int* flag = p.rn.ready + ray;
+            if (*flag == 0) {
+              const long long t0 = clock64();
+              while (*flag == 0) {
+                if (*(volatile int*)p.status != 0) break;
+                if (clock64() - t0 > TIMEOUT_CYCLES) {
+                  atomicCAS(p.status, 0, 160);
+                  if (((volatile int*)p.status)[1]) __trap();
+                  break;
+                }
+              }
+            }
+            __threadfence();
+            zz = __ldcg(p.rn.zf + pt);
           }
-          uint8_t* row_hi = smem + SM_A + grow * 128;
-          uint8_t* row_lo = row_hi + 8192;
+          for (int i = 0; i < 3; ++i) {
+            d[i] = rr[3 + i];
+            x[i] = __fadd_rn(rr[i], __fmul_rn(zz, d[i]));  // nerf.py:185
+          }
+        } else {
+          load_point(p.src, pt, x, d);
+        }
+        for (int v = 0; v < NS; ++v) {
+          // ---- geometry + the 42 input channels -> A chunk 0 (lin_in operand) ----
+          {
+            PointGeom pg = point_geometry(p.sc, sb, v, x, d);
+            if (gsub == 0) {
+              uint32_t* geo = reinterpret_cast<uint32_t*>(smem + SM_GEO) + grow * 8;
+              const uint32_t vbase = (uint32_t)(sb * NS + v) * p.sc.Hl * p.sc.Wl;
+              geo[0] = (vbase + pg.y0 * p.sc.Wl + pg.x0) * D;
+              geo[1] = (vbase + pg.y0 * p.sc.Wl + pg.x1) * D;
+              geo[2] = (vbase + pg.y1 * p.sc.Wl + pg.x0) * D;
+              geo[3] = (vbase + pg.y1 * p.sc.Wl + pg.x1) * D;
+              geo[4] = __float_as_uint(pg.w_nw);
+              geo[5] = __float_as_uint(pg.w_ne);
+              geo[6] = __float_as_uint(pg.w_sw);
+              geo[7] = __float_as_uint(pg.w_se);
+            }
+            uint8_t* row_hi = smem + SM_A + grow * 128;
+            uint8_t* row_lo = row_hi + 8192;
 #pragma unroll 1
-          for (int e = 0; e < 6; e += 2) {
-            const int ch = gsub * 6 + e;
-            float f0 = feat_channel(pg, ch), f1 = feat_channel(pg, ch + 1);
-            f0 = fmaxf(fminf(f0, 65504.f), -65504.f);
-            f1 = fmaxf(fminf(f1, 65504.f), -65504.f);
-            __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-            __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
-            const uint32_t hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            const uint32_t lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            const int byte = ((ch >> 3) ^ (grow & 7)) * 16 + (ch & 7) * 2;
-            *reinterpret_cast<uint32_t*>(row_hi + byte) = hi;
-            *reinterpret_cast<uint32_t*>(row_lo + byte) = lo;
+            for (int e = 0; e < 6; e += 2) {
+              const int ch = gsub * 6 + e;
+              float f0 = feat_channel(pg, ch), f1 = feat_channel(pg, ch + 1);
+              f0 = fmaxf(fminf(f0, 65504.f), -65504.f);
+              f1 = fmaxf(fminf(f1, 65504.f), -65504.f);
+              __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+              __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
+              const uint32_t hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              const uint32_t lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              const int byte = ((ch >> 3) ^ (grow & 7)) * 16 + (ch & 7) * 2;
+              *reinterpret_cast<uint32_t*>(row_hi + byte) = hi;
+              *reinterpret_cast<uint32_t*>(row_lo + byte) = lo;
+            }
+            fence_proxy_async();
+            tc_fence_before();  // this warp's earlier TMEM reads (previous view / tile) precede the next lin_in MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(bar_base + BAR_F_FULL * 8, 0);
+            workers_sync();  // geometry visible to all worker warps
           }
-          fence_proxy_async();
-          tc_fence_before();  // this warp's earlier TMEM reads (previous view / tile) precede the next lin_in MMA
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta(bar_base + BAR_F_FULL * 8, 0);
-          workers_sync();  // geometry visible to all worker warps
-          t_geo += clock64() - tg0;
-        }
-        // ---- lin_in, then blocks 0..2 ----
-        for (int blk = 0; blk < 3; ++blk) {
-          const float* proj_blk = p.proj + (size_t)blk * map_stride;
-          if (blk == 0) {
-            for (int jj = 1; jj < 8; ++jj) stage_gather_chunk(smem, c.smem_u, proj_blk, chunk_order(jj), warp, lane);
+          // ---- lin_in, then blocks 0..2 ----
+          for (int blk = 0; blk < 3; ++blk) {
+            const float* proj_blk = P.proj + (size_t)blk * map_stride;
+            if (blk == 0) {
+              for (int jj = 1; jj < 8; ++jj) stage_gather_chunk(smem, c.smem_u, proj_blk, chunk_order(jj), warp, lane);
+            }
+            epilogue<MODE_GATHER>(c, p, nullptr, X_COL, nullptr, proj_blk, v, nullptr, nullptr, acc_phase, blk != 0,
+                                  (fc_idx - 1) & 1, warp, 100 + 2 * blk);
+            acc_phase ^= 1;
+            ++fc_idx;
+            epilogue<MODE_HIDDEN>(c, p, nullptr, H_COL, P.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_phase, true,
+                                  (fc_idx - 1) & 1, warp, 110 + 2 * blk);
+            acc_phase ^= 1;
+            ++fc_idx;
           }
-          epilogue<MODE_GATHER>(c, p, X_COL, nullptr, proj_blk, v, nullptr, nullptr, acc_phase, blk != 0,
-                                (fc_idx - 1) & 1, warp, 100 + 2 * blk);
+          epilogue<MODE_COMBINE>(c, p, nullptr, X_COL, P.fc1_b[2], nullptr, v, scratch, nullptr, acc_phase, true,
+                                 (fc_idx - 1) & 1, warp, 120);
           acc_phase ^= 1;
-          ++fc_idx;
-          epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[blk], nullptr, v, nullptr, nullptr, acc_phase, true,
-                                (fc_idx - 1) & 1, warp, 110 + 2 * blk);
-          acc_phase ^= 1;
-          ++fc_idx;
+          if (v == NS - 1) ++fc_idx;
         }
-        epilogue<MODE_COMBINE>(c, p, X_COL, p.mlp.fc1_b[2], nullptr, v, scratch, nullptr, acc_phase, true,
-                               (fc_idx - 1) & 1, warp, 120);
+        epilogue<MODE_HIDDEN>(c, p, nullptr, H_COL, P.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                              (fc_idx - 1) & 1, warp, 130);
         acc_phase ^= 1;
-        if (v == NS - 1) ++fc_idx;
-      }
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
-                            (fc_idx - 1) & 1, warp, 130);
-      acc_phase ^= 1;
-      ++fc_idx;
-      epilogue<MODE_BIAS_WB>(c, p, X_COL, p.mlp.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
-                             (fc_idx - 1) & 1, warp, 132);
-      acc_phase ^= 1;
-      ++fc_idx;
-      epilogue<MODE_HIDDEN>(c, p, H_COL, p.mlp.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_phase, true,
-                            (fc_idx - 1) & 1, warp, 134);
-      acc_phase ^= 1;
-      ++fc_idx;
-      epilogue<MODE_OUT>(c, p, X_COL, p.mlp.fc1_b[4], nullptr, 0, nullptr, out_part, acc_phase, false, 0, warp, 136);
-      acc_phase ^= 1;
-      tc_fence_before();
-      workers_sync();
-      if (threadIdx.x < ROWS) {
-        const int64_t opt = tile * TILE_POINTS + rank * ROWS + threadIdx.x;
-        if (opt < p.total_points) {
-          const float4* pp = reinterpret_cast<const float4*>(out_part) + threadIdx.x * 8;
-          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        ++fc_idx;
+        epilogue<MODE_BIAS_WB>(c, p, nullptr, X_COL, P.fc1_b[3], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                               (fc_idx - 1) & 1, warp, 132);
+        acc_phase ^= 1;
+        ++fc_idx;
+        epilogue<MODE_HIDDEN>(c, p, nullptr, H_COL, P.fc0_b[4], nullptr, 0, nullptr, nullptr, acc_phase, true,
+                              (fc_idx - 1) & 1, warp, 134);
+        acc_phase ^= 1;
+        ++fc_idx;
+        epilogue<MODE_OUT>(c, p, P.lin_out_w, X_COL, P.fc1_b[4], nullptr, 0, nullptr, out_part, acc_phase, false, 0,
+                           warp, 136);
+        acc_phase ^= 1;
+        tc_fence_before();
+        workers_sync();
+        if (threadIdx.x < ROWS) {
+          const int64_t opt = tile * TILE_POINTS + rank * ROWS + threadIdx.x;
+          if (opt < P.total_points) {
+            const float4* pp = reinterpret_cast<const float4*>(out_part) + threadIdx.x * 8;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 a = pp[k];
-            r0 += a.x; r1 += a.y; r2 += a.z; r3 += a.w;
+            for (int k = 0; k < 8; ++k) {
+              const float4 a = pp[k];
+              r0 += a.x; r1 += a.y; r2 += a.z; r3 += a.w;
+            }
+            const float* bo = P.lin_out_b;
+            r0 += bo[0]; r1 += bo[1]; r2 += bo[2]; r3 += bo[3];
+            float4 o;
+            o.x = 1.0f / (1.0f + expf(-r0));   // sigmoid rgb, relu sigma (models.py:260-264)
+            o.y = 1.0f / (1.0f + expf(-r1));
+            o.z = 1.0f / (1.0f + expf(-r2));
+            o.w = fmaxf(r3, 0.f);
+            reinterpret_cast<float4*>(P.out)[opt] = o;
+            if (render) __threadfence();   // visible device-wide before this ray's completion count moves
           }
-          const float* bo = p.mlp.lin_out_b;
-          r0 += bo[0]; r1 += bo[1]; r2 += bo[2]; r3 += bo[3];
-          float4 o;
-          o.x = 1.0f / (1.0f + expf(-r0));   // sigmoid rgb, relu sigma (models.py:260-264)
-          o.y = 1.0f / (1.0f + expf(-r1));
-          o.z = 1.0f / (1.0f + expf(-r2));
-          o.w = fmaxf(r3, 0.f);
-          reinterpret_cast<float4*>(p.out)[opt] = o;
+        }
+        workers_sync();  // out_part is reused by the next tile; all field values of the tile are stored and fenced
+        if (render && threadIdx.x < ROWS) {
+          // ray completion: the first row of every ray segment inside this CTA's 64 rows adds the segment's length to
+          // the ray's counter; whoever brings it to K owns the ray's compositing (and resampling)
+          const int64_t opt = tile * TILE_POINTS + rank * ROWS + threadIdx.x;
+          if (opt < P.total_points) {
+            const int64_t ray = opt / P.K;
+            const int k = (int)(opt - ray * P.K);
+            if (k == 0 || threadIdx.x == 0) {
+              int64_t seg = P.K - k;
+              if (seg > ROWS - (int)threadIdx.x) seg = ROWS - (int)threadIdx.x;
+              if (seg > P.total_points - opt) seg = P.total_points - opt;
+              const int old = atomicAdd(p.rn.count + (size_t)ps * p.rn.R + ray, (int)seg);
+              if (old + (int)seg == P.K) {
+                const int idx = atomicAdd(n_list, 1);
+                p.rn.lists[(size_t)blockIdx.x * p.rn.cap + idx] = (int)ray;
+              }
+            }
+          }
         }
       }
-      workers_sync();  // out_part is reused by the next tile
+      if (render) {
+        // ---- flush: finish the rays whose last field value this CTA stored (A buffer is idle: per-warp scratch) ----
+        workers_sync();
+        const int n_done = *reinterpret_cast<volatile int*>(n_list);
+        __threadfence();   // acquire side of the completion counters
+        float* fs = reinterpret_cast<float*>(smem + SM_A + warp * FLUSH_SCRATCH_BYTES);
+        for (int i = warp; i < n_done; i += NWORKER_WARPS)
+          finish_ray(p, ps, p.rn.lists[(size_t)blockIdx.x * p.rn.cap + i], fs, lane);
+        workers_sync();
+        if (threadIdx.x == 0) *n_list = 0;
+        // (the next pass's first write to n_list happens after several workers_sync of its first tile)
+      }
     }
   } else if (warp == WARP_MMA) {
     if (rank == 0) {
@@ -606,17 +740,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
         }
         a_phase ^= 1;
       };
-      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-        for (int v = 0; v < NS; ++v) {
-          run_lin_in();
-          for (int blk = 0; blk < 3; ++blk) {
-            run_layer(H_COL, true);              // fc_0
-            run_layer(X_COL, false);             // fc_1 accumulates onto the residual
+      for (int ps = 0; ps < p.npass; ++ps) {
+        const int64_t n_tiles = p.pass[ps].n_tiles;
+        for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+          for (int v = 0; v < NS; ++v) {
+            run_lin_in();
+            for (int blk = 0; blk < 3; ++blk) {
+              run_layer(H_COL, true);              // fc_0
+              run_layer(X_COL, false);             // fc_1 accumulates onto the residual
+            }
           }
-        }
-        for (int blk = 3; blk < 5; ++blk) {
-          run_layer(H_COL, true);
-          run_layer(X_COL, false);
+          for (int blk = 3; blk < 5; ++blk) {
+            run_layer(H_COL, true);
+            run_layer(X_COL, false);
+          }
         }
       }
       if (lane == 0) {
@@ -632,12 +769,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       uint32_t seq = 0;
       long long t_fwd = 0;
       const uint32_t per_tile = (uint32_t)NS * (SLOTS_LIN_IN + 6 * SLOTS_FC) + 4 * SLOTS_FC;
-      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-        for (uint32_t i = 0; i < per_tile; ++i) {
-          const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
-          mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl, t_fwd);
-          mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
-          ++seq;
+      for (int ps = 0; ps < p.npass; ++ps) {
+        const int64_t n_tiles = p.pass[ps].n_tiles;
+        for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+          for (uint32_t i = 0; i < per_tile; ++i) {
+            const uint32_t sl = seq % NSLOTS, ph = (seq / NSLOTS) & 1;
+            mbar_wait_spin(bar_base + (BAR_B_FULL + sl) * 8, ph, p.status, 300 + sl, t_fwd);
+            mbar_arrive_cta(bar_base + (BAR_B_PEER + sl) * 8, 0);
+            ++seq;
+          }
         }
       }
     }
@@ -647,6 +787,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
       uint32_t seq = 0;
       long long t_empty = 0;
       const uint32_t b_base = smem_u32(smem + SM_B);
+      const uint8_t* slots = nullptr;
       // (a bulk copy cannot complete on a barrier of another CTA than its destination -- tried, it faults -- so each
       //  CTA streams its own half and the peer forwards "landed" to the leader)
       auto stream_slot = [&](int slot_index) {
@@ -665,12 +806,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
           stream_slot(base + chunk_order(jj) * 4 + b * 2 + 1);
         }
       };
-      for (int64_t tile = pair; tile < p.n_tiles; tile += n_pairs) {
-        for (int v = 0; v < NS; ++v) {
-          for (int r = 0; r < SLOTS_LIN_IN; ++r) stream_slot(r);
-          for (int l = 0; l < 6; ++l) stream_fc(l);
+      for (int ps = 0; ps < p.npass; ++ps) {
+        slots = p.pass[ps].packed + HEADER_BYTES + (size_t)rank * SLOTS_PER_RANK * SLOT_BYTES;
+        const int64_t n_tiles = p.pass[ps].n_tiles;
+        for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+          for (int v = 0; v < NS; ++v) {
+            for (int r = 0; r < SLOTS_LIN_IN; ++r) stream_slot(r);
+            for (int l = 0; l < 6; ++l) stream_fc(l);
+          }
+          for (int l = 6; l < 10; ++l) stream_fc(l);
         }
-        for (int l = 6; l < 10; ++l) stream_fc(l);
       }
       if (rank == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.status + 2) + 7, (unsigned long long)t_empty);
     }
@@ -779,6 +924,40 @@ size_t tc_workspace_bytes(const PnrScene&, const PnrMlp&, int64_t total_points) 
   return (size_t)tc_pairs(n_tiles) * 2 * tc::D * tc::ROWS * sizeof(float) + 1024;
 }
 
+static void fill_pass(tc::Pass& P, const PnrMlp& mlp, const float* proj, float* out, int64_t total_points, int64_t P_obj,
+                      int K) {
+  P.packed = static_cast<const uint8_t*>(mlp.packed);
+  P.proj = proj;
+  for (int i = 0; i < 5; ++i) {
+    P.fc0_b[i] = mlp.fc0_b[i];
+    P.fc1_b[i] = mlp.fc1_b[i];
+  }
+  P.lin_out_w = mlp.lin_out_w;
+  P.lin_out_b = mlp.lin_out_b;
+  P.out = out;
+  P.total_points = total_points;
+  P.n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+  P.P = P_obj;
+  P.K = K;
+}
+
+static int tc_launch(tc::Params& p, int pairs, cudaStream_t s) {
+  int rc = tc::get_status_buffer(&p.status);
+  if (rc) return rc;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    PNR_CUDA(cudaFuncSetAttribute(tc::k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  prof_before(s);
+  tc::k_field_tc<<<dim3(pairs * 2), dim3(tc::NTHREADS), tc::SMEM_BYTES, s>>>(p);
+  prof_after(s);
+  PNR_LAUNCH_CHECK();
+  return PNR_OK;
+}
+
 int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, const PointSource& src,
                   int64_t total_points, float* out, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (!tc_supported(sc, mlp) || !mlp.packed || !proj) {
@@ -794,31 +973,100 @@ int tc_field_eval(const PnrScene& sc, const PnrMlp& mlp, const float* proj, cons
     return PNR_ERR_WORKSPACE;
   }
   if (total_points == 0) return PNR_OK;
-  tc::Params p;
+  tc::Params p{};
   p.sc = sc;
   p.src = src;
-  p.mlp = mlp;
-  p.packed = static_cast<const uint8_t*>(mlp.packed);
-  p.proj = proj;
+  p.npass = 1;
+  fill_pass(p.pass[0], mlp, proj, out, total_points, src.P, src.K > 0 ? src.K : 1);
+  p.rn.rays = nullptr;
   p.scratch = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  p.out = out;
-  p.total_points = total_points;
-  p.n_tiles = (total_points + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
-  int rc = tc::get_status_buffer(&p.status);
-  if (rc) return rc;
-  const int pairs = tc_pairs(p.n_tiles);
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev]) {
-    PNR_CUDA(cudaFuncSetAttribute(tc::k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    attr_set[dev] = true;
+  return tc_launch(p, tc_pairs(p.pass[0].n_tiles), s);
+}
+
+// ---- fused render: NeRFRenderer.forward (nerf.py:251-303) in ONE launch of the tensor engine ----------------------
+// Workspace: view-sum scratch | field values of both passes | completion counters + ready flags | completion lists.
+static int tc_render_pairs(int64_t R, int Kc, int K) {
+  const int64_t tiles = ((int64_t)R * (K > Kc ? K : Kc) + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+  return tc_pairs(tiles);
+}
+static int tc_render_cap(int64_t R, int Kc, int K, int pairs) {
+  // rays a CTA can complete in one pass: (tiles per pair) x (rays that end inside 64 rows)
+  int64_t cap = 0;
+  for (int Kp : {Kc, K}) {
+    if (Kp <= 0) continue;
+    const int64_t tiles = (R * Kp + tc::TILE_POINTS - 1) / tc::TILE_POINTS;
+    const int64_t per_pair = (tiles + pairs - 1) / pairs;
+    const int64_t c = per_pair * (tc::ROWS / Kp + 2);
+    if (c > cap) cap = c;
   }
-  prof_before(s);
-  tc::k_field_tc<<<dim3(pairs * 2), dim3(tc::NTHREADS), tc::SMEM_BYTES, s>>>(p);
-  prof_after(s);
-  PNR_LAUNCH_CHECK();
-  return PNR_OK;
+  return (int)(cap + 8);
+}
+
+size_t tc_render_workspace_bytes(const PnrScene& sc, int64_t R, int Kc, int Kf) {
+  const int K = Kc + Kf;
+  const int pairs = tc_render_pairs(R, Kc, K);
+  size_t b = (size_t)pairs * 2 * tc::D * tc::ROWS * sizeof(float) + 1024;
+  b += align_up((size_t)R * Kc * 16, 256) + align_up((size_t)R * K * 16, 256);
+  b += align_up((size_t)R * 3 * sizeof(int), 256);
+  b += align_up((size_t)pairs * 2 * tc_render_cap(R, Kc, K, pairs) * sizeof(int), 256);
+  return b + 1024;
+}
+
+int tc_render(const PnrScene& sc, const PnrMlp& mc, const PnrMlp& mf, const float* proj_c, const float* proj_f,
+              const PnrRenderCfg& cfg, const float* rays, const PnrNoise& noise, float* zc, float* wc, float* zf,
+              const PnrRenderOut& out, int64_t B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const int64_t R = B * sc.SB;
+  const int Kc = cfg.n_coarse, Kf = cfg.n_fine, Kfd = cfg.n_fine_depth, K = Kc + Kf;
+  if (ws_bytes < tc_render_workspace_bytes(sc, R, Kc, Kf)) {
+    set_error("workspace too small for the fused render");
+    return PNR_ERR_WORKSPACE;
+  }
+  if (K > 512) {
+    set_error("n_coarse + n_fine = %d exceeds 512", K);
+    return PNR_ERR_INVALID;
+  }
+  if ((int64_t)R * K >= (1ll << 31)) {
+    set_error("too many sample points for one fused render call (R * K must stay below 2^31)");
+    return PNR_ERR_INVALID;
+  }
+  const int pairs = tc_render_pairs(R, Kc, K);
+  Arena ar(ws, ws_bytes);
+  tc::Params p{};
+  p.sc = sc;
+  p.scratch = ar.take<float>((size_t)pairs * 2 * tc::D * tc::ROWS);
+  float* field_c = ar.take<float>((size_t)R * Kc * 4);
+  float* field_f = ar.take<float>((size_t)R * K * 4);
+  int* flags = ar.take<int>((size_t)R * 3);
+  p.rn.cap = tc_render_cap(R, Kc, K, pairs);
+  p.rn.lists = ar.take<int>((size_t)pairs * 2 * p.rn.cap);
+  PNR_CUDA(cudaMemsetAsync(flags, 0, (size_t)R * 3 * sizeof(int), s));
+  p.npass = Kf > 0 ? 2 : 1;
+  fill_pass(p.pass[0], mc, proj_c, field_c, R * Kc, B * Kc, Kc);
+  if (Kf > 0) fill_pass(p.pass[1], mf, proj_f, field_f, R * K, B * K, K);
+  tc::Render& rn = p.rn;
+  rn.rays = rays;
+  rn.lin = noise.lin_steps;
+  rn.u_c = noise.u_coarse;
+  rn.u_f = noise.u_fine;
+  rn.u_j = noise.u_fine_jit;
+  rn.n_d = noise.n_depth;
+  rn.zc = zc;
+  rn.wc = wc;
+  rn.zf = zf;
+  rn.rgb_c = out.rgb_coarse;
+  rn.depth_c = out.depth_coarse;
+  rn.rgb_f = out.rgb_fine;
+  rn.depth_f = out.depth_fine;
+  rn.w_f = out.weights_fine;
+  rn.count = flags;
+  rn.ready = flags + 2 * R;
+  rn.R = R;
+  rn.Kc = Kc;
+  rn.Kf = Kf;
+  rn.Kfd = Kfd;
+  rn.white = cfg.white_bkgd;
+  rn.depth_std = cfg.depth_std;
+  return tc_launch(p, pairs, s);
 }
 
 }  // namespace pnr

@@ -28,8 +28,14 @@ __device__ __forceinline__ float coarse_sample(float near, float far, float lin_
 }
 
 // Alpha compositing of one ray (nerf.py:178-182, 222-249), sequential transmittance product like torch.cumprod on the
-// CPU.  zr [K], fr [K] = (sigmoid rgb, relu sigma); w_out may be NULL.  LOAD abstracts the load flavour (the fused
-// kernel reads values other CTAs wrote and must bypass L1).
+// CPU.  zr [K], fr [K] = (sigmoid rgb, relu sigma); w_out may be NULL.  ldf / ldf4 abstract the load flavour (the
+// fused kernel reads values other CTAs wrote during the same launch and must bypass L1).
+struct LdPlain {
+  __device__ __forceinline__ float operator()(const float* q) const { return *q; }
+};
+struct LdPlain4 {
+  __device__ __forceinline__ float4 operator()(const float4* q) const { return *q; }
+};
 template <typename LoadF, typename LoadF4>
 __device__ __forceinline__ void composite_ray(const float* zr, const float4* fr, float far, int K, int white,
                                               float* w_out, float* rgb_out, float* depth_out, LoadF ldf, LoadF4 ldf4) {
@@ -66,17 +72,19 @@ __device__ __forceinline__ void composite_ray(const float* zr, const float4* fr,
 //   zc, wc [Kc]: the coarse samples and weights; dc: coarse depth; u, uj [Kf-Kfd]; nd [Kfd]; zout [Kc+Kf] ascending.
 //   scratch: Kc + 1 + Kc + Kf floats of shared memory private to the warp.
 // cdf is accumulated sequentially (torch.cumsum order on CPU).
+template <typename LoadF>
 __device__ __forceinline__ void sample_fine_ray(float near, float far, const float* zc, const float* wc, float dc,
                                                 const float* u, const float* uj, const float* nd, float depth_std,
-                                                float* zout, int Kc, int Kf, int Kfd, float* scratch, int lane) {
+                                                float* zout, int Kc, int Kf, int Kfd, float* scratch, int lane,
+                                                LoadF ldf) {
   const int K = Kc + Kf, Ku = Kf - Kfd;
   float* cdf = scratch;            // [Kc+1]
   float* zs = scratch + (Kc + 1);  // [K]
-  for (int k = lane; k < Kc; k += 32) zs[k] = zc[k];
+  for (int k = lane; k < Kc; k += 32) zs[k] = ldf(zc + k);
   if (Ku > 0) {
     // pdf = (w + 1e-5) / sum ; cdf = [0, cumsum(pdf)]
     float part = 0.f;
-    for (int k = lane; k < Kc; k += 32) part = __fadd_rn(part, __fadd_rn(wc[k], 1e-5f));
+    for (int k = lane; k < Kc; k += 32) part = __fadd_rn(part, __fadd_rn(ldf(wc + k), 1e-5f));
     // torch.sum order is not sequential either; use a fixed tree so results are deterministic
     for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, o));
     const float total = part;
@@ -84,7 +92,7 @@ __device__ __forceinline__ void sample_fine_ray(float near, float far, const flo
       float acc = 0.f;
       cdf[0] = 0.f;
       for (int k = 0; k < Kc; ++k) {
-        acc = __fadd_rn(acc, __fdiv_rn(__fadd_rn(wc[k], 1e-5f), total));
+        acc = __fadd_rn(acc, __fdiv_rn(__fadd_rn(ldf(wc + k), 1e-5f), total));
         cdf[k + 1] = acc;
       }
     }

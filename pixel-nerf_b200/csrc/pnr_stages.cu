@@ -9,6 +9,7 @@
 
 #include "pnr_common.cuh"
 #include "pnr_geom.cuh"
+#include "pnr_ray_ops.cuh"
 
 namespace pnr {
 
@@ -43,25 +44,13 @@ int launch_pack_latent(const float* nchw, float* nhwc, int V, int C, int Hl, int
 // ----------------------------------------------------------------------------------------
 // sample_coarse (src/render/nerf.py:98-113)
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ float lin_step_value(int k, int Kc) {
-  // torch.linspace(0, 1 - 1/Kc, Kc) in fp32 (symmetric two-sided formula of ATen)
-  float step_sz = 1.0f / (float)Kc;
-  float end = 1.0f - step_sz;
-  float inc = (Kc > 1) ? end / (float)(Kc - 1) : 0.f;
-  return (k < Kc / 2) ? inc * (float)k : end - inc * (float)(Kc - 1 - k);
-}
-
 __global__ void k_sample_coarse(const float* __restrict__ rays, const float* __restrict__ lin,
                                 const float* __restrict__ u, float* __restrict__ z, int64_t R, int Kc) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * Kc) return;
   int64_t r = i / Kc;
   int k = (int)(i - r * Kc);
-  float near = rays[r * 8 + 6], far = rays[r * 8 + 7];
-  float step = 1.0f / (float)Kc;  // python float 1.0/Kc rounded to fp32 on use
-  float s = lin ? lin[k] : lin_step_value(k, Kc);
-  s = s + u[i] * step;            // z_steps += rand_like * step
-  z[i] = near * (1.0f - s) + far * s;
+  z[i] = coarse_sample(rays[r * 8 + 6], rays[r * 8 + 7], lin ? lin[k] : lin_step_value(k, Kc), u[i], Kc);
 }
 
 int launch_sample_coarse(const float* rays, const float* lin, const float* u, float* z, int64_t R, int Kc,
@@ -81,36 +70,8 @@ __global__ void k_composite(const float* __restrict__ rays, const float* __restr
                             float* __restrict__ rgb_out, float* __restrict__ depth_out, int64_t R, int K) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  const float far = rays[r * 8 + 7];
-  const float* zr = z + r * K;
-  const float4* fr = reinterpret_cast<const float4*>(field) + r * K;
-  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, wsum = 0.f;
-  float zk = zr[0];
-  for (int k = 0; k < K; ++k) {
-    float znext = (k + 1 < K) ? zr[k + 1] : far;
-    float delta = znext - zk;
-    float4 f = fr[k];
-    float sigma = fmaxf(f.w, 0.f);
-    float alpha = 1.0f - expf(-delta * sigma);
-    float w = alpha * T;
-    T = T * ((1.0f - alpha) + 1e-10f);
-    cr += w * f.x;
-    cg += w * f.y;
-    cb += w * f.z;
-    cd += w * zk;
-    wsum += w;
-    if (w_out) w_out[r * K + k] = w;
-    zk = znext;
-  }
-  if (white) {
-    cr = (cr + 1.0f) - wsum;
-    cg = (cg + 1.0f) - wsum;
-    cb = (cb + 1.0f) - wsum;
-  }
-  rgb_out[r * 3 + 0] = cr;
-  rgb_out[r * 3 + 1] = cg;
-  rgb_out[r * 3 + 2] = cb;
-  depth_out[r] = cd;
+  composite_ray(z + r * K, reinterpret_cast<const float4*>(field) + r * K, rays[r * 8 + 7], K, white,
+                w_out ? w_out + r * K : nullptr, rgb_out + r * 3, depth_out + r, LdPlain(), LdPlain4());
 }
 
 int launch_composite(const float* rays, const float* z, const float* field, int white, float* w,
@@ -135,62 +96,13 @@ __global__ void k_sample_fine(const float* __restrict__ rays, const float* __res
   extern __shared__ float sm[];
   const int warps = blockDim.x / 32;
   const int wid = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int K = Kc + Kf;
-  float* cdf = sm + (size_t)wid * (Kc + 1 + K);  // [Kc+1]
-  float* zs = cdf + (Kc + 1);                     // [K]
+  const int K = Kc + Kf, Ku = Kf - Kfd;
+  float* scratch = sm + (size_t)wid * (Kc + 1 + K);
   int64_t r = (int64_t)blockIdx.x * warps + wid;
   if (r >= R) return;
-  const float near = rays[r * 8 + 6], far = rays[r * 8 + 7];
-  const int Ku = Kf - Kfd;
-
-  for (int k = lane; k < Kc; k += 32) zs[k] = zc[r * Kc + k];
-  if (Ku > 0) {
-    // pdf = (w + 1e-5) / sum ; cdf = [0, cumsum(pdf)]
-    float part = 0.f;
-    for (int k = lane; k < Kc; k += 32) part += wc[r * Kc + k] + 1e-5f;
-    // torch.sum order is not sequential either; use a fixed tree so results are deterministic
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const float total = part;
-    if (lane == 0) {
-      float acc = 0.f;
-      cdf[0] = 0.f;
-      for (int k = 0; k < Kc; ++k) {
-        acc += (wc[r * Kc + k] + 1e-5f) / total;
-        cdf[k + 1] = acc;
-      }
-    }
-    __syncwarp();
-    for (int j = lane; j < Ku; j += 32) {
-      float uu = u[r * Ku + j];
-      // searchsorted(cdf, u, right=True): number of entries <= u  (cdf is non-decreasing)
-      int lo = 0, hi = Kc + 1;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
-      }
-      float ind = fmaxf((float)lo - 1.0f, 0.f);
-      float s = (ind + uj[r * Ku + j]) / (float)Kc;
-      zs[Kc + j] = near * (1.0f - s) + far * s;
-    }
-  }
-  if (Kfd > 0) {
-    float d = dc[r];
-    for (int j = lane; j < Kfd; j += 32) {
-      float zz = d + nd[r * Kfd + j] * depth_std;
-      zs[Kc + Ku + j] = fmaxf(fminf(zz, far), near);
-    }
-  }
-  __syncwarp();
-  // rank sort (values only matter; ties broken by index)
-  for (int i = lane; i < K; i += 32) {
-    float v = zs[i];
-    int rank = 0;
-    for (int j = 0; j < K; ++j) {
-      float o = zs[j];
-      rank += (o < v) || (o == v && j < i);
-    }
-    zout[r * K + rank] = v;
-  }
+  sample_fine_ray(rays[r * 8 + 6], rays[r * 8 + 7], zc + r * Kc, wc ? wc + r * Kc : nullptr, (Kfd > 0) ? dc[r] : 0.f,
+                  u ? u + r * Ku : nullptr, uj ? uj + r * Ku : nullptr, nd ? nd + r * Kfd : nullptr, depth_std,
+                  zout + r * K, Kc, Kf, Kfd, scratch, lane, LdPlain());
 }
 
 int launch_sample_fine(const float* rays, const float* zc, const float* wc, const float* dc,

@@ -30,11 +30,42 @@ def split_top(s):
 
 
 KDEF = re.compile(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(")
+DDEF = re.compile(r"__device__\s+(?:__forceinline__\s+)?[\w:<>]+[\s\*&]+(\w+)\s*\(")
+
+
+def _body(text, start):
+    i = text.find("{", start)
+    j = text.find(";", start)
+    if i < 0 or (0 <= j < i):
+        return None
+    depth, k = 0, i
+    while True:
+        depth += text[k] == "{"
+        depth -= text[k] == "}"
+        k += 1
+        if depth == 0:
+            return text[i:k]
+
+
+def warp_collective_helpers():
+    """Names of __device__ functions in the shared headers that use warp collectives: a kernel calling one of them
+    needs its threads run as warps even if its own body does not mention __shfl / __syncwarp."""
+    names = set()
+    for name in sorted(os.listdir(CSRC)):
+        if not name.endswith(".cuh") or name == "pnr_tc_ptx.cuh":
+            continue
+        text = open(os.path.join(CSRC, name)).read()
+        for m in DDEF.finditer(text):
+            body = _body(text, m.end())
+            if body and ("__shfl" in body or "__syncwarp" in body):
+                names.add(m.group(1))
+    return names
 
 
 def classify(texts):
     """kernel name -> emu::Mode, from what the kernel body uses."""
     modes = {}
+    helpers = warp_collective_helpers()
     for text in texts:
         for m in KDEF.finditer(text):
             i = text.find("{", m.end())
@@ -51,7 +82,7 @@ def classify(texts):
             body = text[i:k]
             if "__syncthreads" in body:
                 modes[m.group(1)] = "emu::BLOCK"
-            elif "__shfl" in body or "__syncwarp" in body:
+            elif "__shfl" in body or "__syncwarp" in body or any(re.search(r"\b%s\s*\(" % h, body) for h in helpers):
                 modes[m.group(1)] = "emu::WARP"
             else:
                 modes[m.group(1)] = "emu::SEQ"

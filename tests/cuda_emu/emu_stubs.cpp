@@ -10,6 +10,23 @@ int tc_field_eval(const PnrScene&, const PnrMlp&, const float*, const PointSourc
   set_error("tensor engine is not available in the emulator build");
   return PNR_ERR_UNSUPPORTED;
 }
+size_t tc_render_workspace_bytes(const PnrScene&, int64_t, int, int) { return 0; }
+int tc_render(const PnrScene&, const PnrMlp&, const PnrMlp&, const float*, const float*, const PnrRenderCfg&, const float*,
+              const PnrNoise&, float*, float*, float*, const PnrRenderOut&, int64_t, void*, size_t, cudaStream_t) {
+  set_error("tensor engine is not available in the emulator build");
+  return PNR_ERR_UNSUPPORTED;
+}
+// the backward's GEMMs run on the fp32 SIMT SGEMM in the emulator (the tcgen05 GEMM has no host meaning)
+int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, bool relu_a,
+          bool accum, cudaStream_t s);
+int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+                bool relu_a, bool accum, cudaStream_t s) {
+  if (ldw != K) {
+    set_error("emulator gemm: ldw must equal K");
+    return PNR_ERR_INVALID;
+  }
+  return sgemm(A, lda, W, bias, C, ldc, M, N, K, relu_a, accum, s);
+}
 }  // namespace pnr
 
 extern "C" {
