@@ -214,6 +214,38 @@ size_t pnr_project_latent_bytes(const PnrScene* scene, const PnrMlp* mlp);
 int pnr_project_latent(const PnrScene* scene, const PnrMlp* mlp, float* proj, size_t proj_bytes,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- single-process multi-GPU driver: replaces nn.DataParallel(_RenderWrapper, gpus, dim=1), nerf.py:354-371 ----
+ * One host thread, n devices of one node.  The read-only scene state is sent once per change (pnr_mgpu_broadcast, peer
+ * copies over NVLink); a render call shards the rays along B with torch.chunk bounds (ceil(B/n) per device, in device
+ * order -- the order DataParallel gathers in), runs ONE pnr_render per device and returns the pixels to device 0.  For a
+ * single object (SB = 1) the final rgb / depth are stored by the kernels directly into the caller's tensors on
+ * device 0 through peer memory; other outputs / SB > 1 come back as strided peer copies.  Asynchronous: the caller's
+ * stream on device 0 waits for the shards.  Errors: as everywhere (negative code + pnr_last_error). */
+typedef struct PnrMgpu PnrMgpu;   /* opaque: device list, events, fallback streams */
+
+typedef struct PnrShard {         /* everything device i needs for its piece of a render call (pointers on device i) */
+  const PnrScene* scene;          /* replica of the scene state on device i (host struct, device pointers)            */
+  const PnrMlp* mlp_coarse;
+  const PnrMlp* mlp_fine;         /* NULL: the coarse MLP serves both passes                                           */
+  const PnrNoise* noise;          /* draws for the shard's SB * B_i rays (device i's generator, as under DataParallel)  */
+  void* workspace;                /* >= pnr_render_workspace_bytes(scene, mlp_coarse, mlp_fine, cfg, B_i)              */
+  size_t workspace_bytes;
+  float* rays_stage;              /* [SB][B_i][8] on device i (unused for shard 0 when SB == 1)                        */
+  PnrRenderOut stage;             /* local outputs [SB*B_i][...]: rgb / depth of both passes required, rest optional  */
+  void* stream;                   /* stream on device i to enqueue on (NULL: the handle's own stream)                  */
+} PnrShard;
+
+int pnr_mgpu_create(const int32_t* device_ids, int32_t n, PnrMgpu** out);   /* enables peer access towards device_ids[0] */
+int pnr_mgpu_destroy(PnrMgpu* h);
+int32_t pnr_mgpu_size(const PnrMgpu* h);
+int32_t pnr_mgpu_peer_store(const PnrMgpu* h, int32_t i);   /* 1 if device i can store into device 0's memory */
+/* dst[i] on device i  <-  src on device 0 (dst[0] ignored, NULL entries skipped); ordered after streams[0] (device 0)
+ * and enqueued on streams[i] (NULL array / entry: the handle's own streams). */
+int pnr_mgpu_broadcast(PnrMgpu* h, const void* src, void* const* dst, size_t bytes, void* const* streams);
+/* rays0 [SB][B][8] and out0 (tensors [SB*B][...], NULL = not wanted) on device 0; shards[n]. */
+int pnr_mgpu_render(PnrMgpu* h, const PnrShard* shards, const PnrRenderCfg* cfg, const float* rays0,
+                    const PnrRenderOut* out0, int64_t B, void* stream0);
+
 /* Test hook for the dense contraction the backward path is built from (nn.Linear forward / input gradient / weight
  * gradient are all this "NT" product): C[M][N] (+)= act(A[M][lda]) * W[N][K]^T (+ bias[N]), fp32 in and out.
  * engine = PNR_ENGINE_SIMT: fp32 FFMA SGEMM; PNR_ENGINE_TC (or AUTO): split-bf16 tcgen05 GEMM (3 products, fp32

@@ -260,7 +260,7 @@ int pnr_field_backward(const PnrScene* scene, const PnrMlp* mlp, const float* xy
 }
 
 static size_t render_bwd_field_ws(const PnrScene& sc, const PnrMlp& m, int64_t pts) {
-  size_t a = simt_workspace_bytes(sc, m, pts), b = field_backward_workspace_bytes(sc, m, pts);
+  size_t a = field_ws(sc, m, pts, PNR_ENGINE_AUTO), b = field_backward_workspace_bytes(sc, m, pts);
   return a > b ? a : b;
 }
 
@@ -328,7 +328,8 @@ int pnr_render_backward(const PnrScene* scene, const PnrMlp* mlp_coarse, const P
     src.z = fwd->z_fine;
     src.K = K;
     src.P = B * K;
-    if ((rc = simt_field_eval(*scene, *m, src, R * K, field, rest, rest_bytes, s))) return rc;
+    const float* pj = mlp_fine ? scene->proj_fine : scene->proj_coarse;
+    if ((rc = field_dispatch(*scene, *m, pj, src, R * K, field, cfg->engine, rest, rest_bytes, s))) return rc;
     if ((rc = launch_composite_bwd(rays, fwd->z_fine, field, d_rgb_fine, nullptr, cfg->white_bkgd, d_field, d_z, R, K, s)))
       return rc;
     if ((rc = field_backward(*scene, *m, src, R * K, d_field, *g, d_latent_nhwc, depth_path ? d_xyz : nullptr, rest,
@@ -342,7 +343,8 @@ int pnr_render_backward(const PnrScene* scene, const PnrMlp* mlp_coarse, const P
   src.z = fwd->z_coarse;
   src.K = Kc;
   src.P = B * Kc;
-  if ((rc = simt_field_eval(*scene, *mlp_coarse, src, R * Kc, field, rest, rest_bytes, s))) return rc;
+  if ((rc = field_dispatch(*scene, *mlp_coarse, scene->proj_coarse, src, R * Kc, field, cfg->engine, rest, rest_bytes, s)))
+    return rc;
   if ((rc = launch_composite_bwd(rays, fwd->z_coarse, field, d_rgb_coarse, depth_path ? d_depth : nullptr,
                                  cfg->white_bkgd, d_field, d_z, R, Kc, s)))
     return rc;

@@ -255,7 +255,7 @@ __global__ void k_geom_bwd(PnrScene sc, PointSource src, int64_t g0, int64_t n_p
 }
 
 static int64_t chunk_points(const PnrScene& sc, int64_t total_points) {
-  int64_t rows = 16384;       // rows per chunk
+  int64_t rows = 32768;       // rows per chunk
   if (const char* e = getenv("PNR_BWD_CHUNK_ROWS")) {   // test hook: force several chunks on small inputs
     const long v = atol(e);
     if (v >= sc.NS) rows = v;

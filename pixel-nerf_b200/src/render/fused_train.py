@@ -95,7 +95,7 @@ class _FusedRender(torch.autograd.Function):
         fwd.z_coarse, fwd.depth_coarse = pn.dptr(z_c.contiguous()), pn.dptr(depth_c.contiguous())
         if fine:
             fwd.z_fine = pn.dptr(z_f.contiguous())
-        cfg = pn.PnrRenderCfg(Kc, Kf, Kfd, depth_std, 1 if white else 0, pn.ENGINE_SIMT)
+        cfg = pn.PnrRenderCfg(Kc, Kf, Kfd, depth_std, 1 if white else 0, pn.ENGINES[model.engine])
         L = pn.lib()
         nbytes = L.pnr_render_backward_workspace_bytes(scene, mc, mf, cfg, B)
         ws = pn.workspace(dev, nbytes)

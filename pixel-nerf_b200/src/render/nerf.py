@@ -102,9 +102,13 @@ class _SceneReplica:
         self.scene_key = None
         self.refreshes = 0          # (weights, scene) copies made so far: tests and DESIGN.md quote it
 
-    def refresh(self, net, want_fine):
+    def refresh(self, net, want_fine, send=None):
+        """send(tensor, device) -> copy on `device`; default torch's `.to` (a peer copy as well).  `_ShardedRender` passes
+        a sender built on pnr_mgpu_broadcast for the large buffers."""
         from model.models import _param_key
         dev = self.device
+        if send is None:
+            send = lambda t, d: t.to(d, non_blocking=True)
         self.engine = net.engine
         names = ["mlp_coarse"] + (["mlp_fine"] if (want_fine and net.mlp_fine is not None) else [])
         scene0, _, _, (nhwc0, proj0) = net._scene_struct(want_fine=want_fine)   # primary: packs / projects if stale
@@ -115,7 +119,7 @@ class _SceneReplica:
                 continue
             _, _, sd0, packed0 = net._fused.mlp[name]
             sd = {k: v.to(dev, non_blocking=True) for k, v in sd0.items()}
-            packed = packed0.to(dev, non_blocking=True) if packed0 is not None else None
+            packed = send(packed0, dev) if packed0 is not None else None
             struct = pn.make_mlp_struct(sd, mlp.d_in, mlp.d_latent, mlp.d_hidden, mlp.d_out, mlp.n_blocks,
                                         mlp.combine_layer, packed=packed)
             self.mlp[name], self.mlp_key[name] = (struct, sd, packed), key
@@ -124,8 +128,9 @@ class _SceneReplica:
         skey = (net._scene_epoch, lat.data_ptr(), lat._version, tuple(self.mlp_key.get(n) for n in names), want_fine)
         if skey != self.scene_key:
             to = lambda t: None if t is None else t.to(dev, non_blocking=True)
-            self.nhwc = to(nhwc0)
-            self.proj = {k: to(v) for k, v in proj0.items()}
+            big = lambda t: None if t is None else send(t, dev)
+            self.nhwc = big(nhwc0)
+            self.proj = {k: big(v) for k, v in proj0.items()}
             self.poses, self.focal, self.c = to(net.poses), to(net.focal), to(net.c)
             self.meta = (scene0.SB, scene0.NS, scene0.image_w, scene0.image_h, scene0.scale_x, scene0.scale_y)
             self.scene_key = skey
@@ -141,10 +146,12 @@ class _SceneReplica:
 
 
 class _ShardedRender(torch.nn.Module):
-    """Single-process ray sharding over several GPUs (replaces nn.DataParallel(dim=1), nerf.py:368-370).  Shard i gets
-    torch.chunk piece i of the rays along dim 1 (same ray order as DataParallel); kernels on all devices are enqueued
-    from this thread (launches are asynchronous) and results are copied to gpus[0] in shard order.  GPUs other than
-    gpus[0] render from a `_SceneReplica`.
+    """Single-process ray sharding over several GPUs (replaces nn.DataParallel(dim=1), nerf.py:368-370) on the C-ABI
+    driver `pnr_mgpu_*` (csrc/pnr_mgpu.cu).  Shard i gets torch.chunk piece i of the rays along dim 1 (same ray order as
+    DataParallel); one host thread enqueues, per GPU, the peer copy of its rays, ONE fused render launch and the return
+    of its pixels -- for a single object the kernels store the final rgb / depth straight into the output tensors on
+    gpus[0] through peer memory.  GPUs other than gpus[0] render from a `_SceneReplica`; every GPU draws its samples
+    from its own generator (as under DataParallel).
 
     Gradient mode (train/train.py with several --gpu_id): the autograd graph lives on gpus[0], so the step runs there
     alone (with a one-time warning) -- replicas hold detached copies and would drop the shards' gradients."""
@@ -155,11 +162,45 @@ class _ShardedRender(torch.nn.Module):
         self.gpus = [int(g) for g in gpus]
         self._replicas = {g: _SceneReplica(torch.device("cuda", g)) for g in self.gpus[1:]}
         self._warned = False
+        self._handle = None
+
+    def _mgpu(self):
+        if self._handle is None:
+            import ctypes as C
+            h = C.c_void_p()
+            ids = (C.c_int32 * len(self.gpus))(*self.gpus)
+            pn.check(pn.lib().pnr_mgpu_create(ids, len(self.gpus), C.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def _send(self, t, dev):
+        """One buffer of the primary device to `dev` through pnr_mgpu_broadcast (peer copy over NVLink, enqueued on
+        torch's current streams so the caching allocator's stream ordering holds)."""
+        import ctypes as C
+        n = len(self.gpus)
+        t = t.contiguous()
+        with torch.cuda.device(dev):
+            dst = torch.empty_like(t, device=dev)
+        ptrs, streams = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for i, g in enumerate(self.gpus):
+            streams[i] = torch.cuda.current_stream(torch.device("cuda", g)).cuda_stream
+            if g == dev.index:
+                ptrs[i] = dst.data_ptr()
+        pn.check(pn.lib().pnr_mgpu_broadcast(self._mgpu(), C.c_void_p(t.data_ptr()), ptrs, t.numel() * t.element_size(),
+                                             streams))
+        return dst
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                pn.lib().pnr_mgpu_destroy(self._handle)
+        except Exception:
+            pass
 
     def forward(self, rays, want_weights=False):
         net, renderer, simple = self.module.net, self.module.renderer, self.module.simple_output
-        if rays.shape[0] == 0 or net._needs_autograd(rays):
-            if rays.shape[0] != 0 and not self._warned:
+        if rays.shape[0] == 0 or rays.shape[1] == 0 or net._needs_autograd(rays):
+            if rays.shape[0] != 0 and rays.shape[1] != 0 and not self._warned:
                 warnings.warn(f"bind_parallel(net, {self.gpus}): gradients are required, so this call runs on cuda:"
                               f"{self.gpus[0]} only (multi-GPU training = one process per GPU)")
                 self._warned = True
@@ -167,30 +208,90 @@ class _ShardedRender(torch.nn.Module):
         if renderer.sched is not None and renderer.last_sched.item() > 0:     # as NeRFRenderer.forward (nerf.py:265-267)
             renderer.n_coarse = renderer.sched[1][renderer.last_sched.item() - 1]
             renderer.n_fine = renderer.sched[2][renderer.last_sched.item() - 1]
-        fine = bool(renderer.using_fine) and int(renderer.n_fine) > 0
+        want_weights = want_weights and not simple
+        Kc, Kf, Kfd = int(renderer.n_coarse), int(renderer.n_fine), int(renderer.n_fine_depth)
+        fine = bool(renderer.using_fine) and Kf > 0
+        if not fine:
+            Kf = Kfd = 0
+        n = len(self.gpus)
         dev0 = torch.device("cuda", self.gpus[0])
-        pieces = torch.chunk(rays, len(self.gpus), dim=1)
-        results = []
-        for g, piece in zip(self.gpus, pieces):
-            if g == self.gpus[0]:
-                results.append(self.module(piece.to(dev0, non_blocking=True), want_weights=want_weights))
+        rays0 = rays.detach().to(dev0).contiguous().float()
+        SB, B, _ = rays0.shape
+        cfg = pn.PnrRenderCfg(Kc, Kf, Kfd, float(renderer.depth_std), 1 if renderer.white_bkgd else 0,
+                              pn.ENGINES[net.engine])
+        L = pn.lib()
+
+        def outputs(dev, rays_per_obj):
+            """PnrRenderOut + DotMap of tensors for SB * rays_per_obj rays on `dev` (as NeRFRenderer._forward_fused)."""
+            R = SB * rays_per_obj
+            f32 = dict(dtype=torch.float32, device=dev)
+            o, res = pn.PnrRenderOut(), DotMap()
+            res.coarse = DotMap(rgb=torch.empty(SB, rays_per_obj, 3, **f32), depth=torch.empty(SB, rays_per_obj, **f32))
+            o.rgb_coarse, o.depth_coarse = pn.dptr(res.coarse.rgb), pn.dptr(res.coarse.depth)
+            if want_weights:
+                res.coarse.weights = torch.empty(SB, rays_per_obj, Kc, **f32)
+                o.weights_coarse = pn.dptr(res.coarse.weights)
+            if fine:
+                res.fine = DotMap(rgb=torch.empty(SB, rays_per_obj, 3, **f32), depth=torch.empty(SB, rays_per_obj, **f32))
+                o.rgb_fine, o.depth_fine = pn.dptr(res.fine.rgb), pn.dptr(res.fine.depth)
+                if want_weights:
+                    res.fine.weights = torch.empty(SB, rays_per_obj, Kc + Kf, **f32)
+                    o.weights_fine = pn.dptr(res.fine.weights)
+            return o, res
+
+        with torch.cuda.device(dev0):
+            out0, res0 = outputs(dev0, B)
+            if simple:                       # only the best pass is returned: do not ship the other one back
+                if fine:
+                    out0.rgb_coarse = out0.depth_coarse = None
+        shards = (pn.PnrShard * n)()
+        keep = []
+        per = -(-B // n)
+        for i, g in enumerate(self.gpus):
+            Bi = min(B, per * (i + 1)) - min(B, per * i)
+            if Bi <= 0:
                 continue
-            rep = self._replicas[g]
-            rep.refresh(net, fine)
-            with torch.cuda.device(rep.device):
-                out = renderer._forward_fused(rep, piece.to(rep.device, non_blocking=True),
-                                              want_weights and not simple)
-            results.append(_wrapper_output(renderer, out, simple))
-        return _gather(results, dev0)
-
-
-def _gather(results, dev):
-    first = results[0]
-    if isinstance(first, dict):
-        return {k: _gather([r[k] for r in results], dev) for k in first}
-    if isinstance(first, (tuple, list)):
-        return type(first)(_gather([r[i] for r in results], dev) for i in range(len(first)))
-    return torch.cat([r.to(dev, non_blocking=True) for r in results], dim=1)
+            dev = torch.device("cuda", g)
+            model = net
+            if i > 0:
+                model = self._replicas[g]
+                model.refresh(net, fine, send=self._send)
+            with torch.cuda.device(dev):
+                scene, mc, mf, keep2 = model._scene_struct(want_fine=fine)
+                Ri = SB * Bi
+                f32 = dict(dtype=torch.float32, device=dev)
+                noise = pn.PnrNoise()            # draws in the reference's order (nerf.py:111,135,141,158)
+                lin = renderer._lin_steps(Kc, dev)
+                u_c = torch.rand(Ri, Kc, **f32)
+                noise.lin_steps, noise.u_coarse = pn.dptr(lin), pn.dptr(u_c)
+                keep += [lin, u_c, keep2, scene, mc, mf, noise]
+                if fine and Kf - Kfd > 0:
+                    u_f, u_j = torch.rand(Ri, Kf - Kfd, **f32), torch.rand(Ri, Kf - Kfd, **f32)
+                    noise.u_fine, noise.u_fine_jit = pn.dptr(u_f), pn.dptr(u_j)
+                    keep += [u_f, u_j]
+                if fine and Kfd > 0:
+                    n_d = torch.randn(Ri, Kfd, **f32)
+                    noise.n_depth = pn.dptr(n_d)
+                    keep.append(n_d)
+                stage, stage_res = outputs(dev, Bi)
+                ws = pn.workspace(dev, L.pnr_render_workspace_bytes(scene, mc, mf, cfg, Bi))
+                sh = shards[i]
+                import ctypes as C
+                sh.scene, sh.mlp_coarse = C.pointer(scene), C.pointer(mc)
+                sh.mlp_fine = C.pointer(mf) if mf is not None else None
+                sh.noise = C.pointer(noise)
+                sh.workspace, sh.workspace_bytes = ws.data_ptr(), ws.numel()
+                if i > 0 or SB > 1:
+                    stage_rays = torch.empty(SB, Bi, 8, **f32)
+                    sh.rays_stage = pn.dptr(stage_rays)
+                    keep.append(stage_rays)
+                sh.stage = stage
+                sh.stream = pn.stream_ptr(dev)
+                keep += [stage_res, ws]
+        with torch.cuda.device(dev0):
+            pn.check(L.pnr_mgpu_render(self._mgpu(), shards, cfg, pn.dptr(rays0, "rays"), out0, B, pn.stream_ptr(dev0)))
+        self._keep = keep        # staging buffers stay referenced until the next call (their streams are still busy)
+        return _wrapper_output(renderer, res0, simple)
 
 
 class NeRFRenderer(torch.nn.Module):
