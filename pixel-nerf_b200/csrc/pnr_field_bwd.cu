@@ -83,18 +83,26 @@ __global__ void k_mask_add(float* __restrict__ D, const float* __restrict__ T, c
   if (i < n && ref[i] > 0.f) D[i] += T[i];
 }
 
-// out[r] += sum_m src[r][m]   (one warp per row)
+// out[r] += sum_m src[r][m]   (one block per row: the rows are few (d <= 512) and long (a chunk's points))
 __global__ void k_rowsum_acc(const float* __restrict__ src, int ld, int n_rows, float* __restrict__ out) {
-  const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32), lane = threadIdx.x % 32;
+  __shared__ float part[8];
+  const int r = blockIdx.x, lane = threadIdx.x % 32, wid = threadIdx.x / 32;
   if (r >= n_rows) return;
   float s = 0.f;
-  for (int m = lane; m < ld; m += 32) s += src[(size_t)r * ld + m];
+  const float* row = src + (size_t)r * ld;
+  for (int m = threadIdx.x; m < ld; m += blockDim.x) s += row[m];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[r] += s;
+  if (lane == 0) part[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x / 32); ++i) t += part[i];
+    out[r] += t;
+  }
 }
 
 static int rowsum_acc(const float* src, int ld, int n_rows, float* out, cudaStream_t s) {
-  k_rowsum_acc<<<(n_rows * 32 + 255) / 256, 256, 0, s>>>(src, ld, n_rows, out);
+  k_rowsum_acc<<<n_rows, 256, 0, s>>>(src, ld, n_rows, out);
   PNR_LAUNCH_CHECK();
   return PNR_OK;
 }

@@ -128,8 +128,18 @@ struct WorkerCtx {
   uint32_t bar_base;    // smem address of the barrier array
   int lane, s, m, n_hi;
   float w_scale, w_inv;
+  uint64_t l2_keep;     // createpolicy evict_last (view-sum scratch)
   long long* t_acc;     // cycles spent waiting for the accumulator barrier
 };
+
+__device__ __forceinline__ void st_evict_last(float* q, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(q), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float ld_evict_last(const float* q, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(q), "l"(pol) : "memory");
+  return v;
+}
 
 // A worker thread owns row m and 8 "steps" of 8 features per layer:
 //   step i -> (b = i>>2 MMA block, c = (i>>1)&1 chunk half, h = i&1): features b*256 + n_hi*128 + c*64 + s*16 + h*8 .. +8
@@ -324,16 +334,19 @@ __device__ __forceinline__ void epilogue(const WorkerCtx& c, const Params& p, co
         y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
       }
       if (MODE == MODE_COMBINE && NS > 1) {
+        // view-sum scratch: 19 MB that every CTA rewrites and re-reads NS-1 times per tile.  Together with the two
+        // MLPs' projected maps and weight images the L2 working set (~140 MB at C2) exceeds the 126 MB L2, and plain
+        // LRU then evicts DIRTY scratch lines to DRAM; evict_last keeps the small hot scratch resident instead
         float* sp = scratch + (size_t)n0 * ROWS + c.m;
         if (view == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
+          for (int e = 0; e < 8; ++e) st_evict_last(sp + e * ROWS, y[e], c.l2_keep);
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = sp[e * ROWS] + y[e];
+          for (int e = 0; e < 8; ++e) y[e] = ld_evict_last(sp + e * ROWS, c.l2_keep) + y[e];
           if (view < NS - 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sp[e * ROWS] = y[e];
+            for (int e = 0; e < 8; ++e) st_evict_last(sp + e * ROWS, y[e], c.l2_keep);
           } else {
             const float ns = (float)NS;
 #pragma unroll
@@ -397,30 +410,51 @@ struct LdCg4 {
 // Fused render: finish ray `ray` of pass `ps` (one warp).  Coarse pass: compositing (nerf.py:222-249), then importance
 // + depth-centred resampling and the sorted merge (nerf.py:120-161, 285-295) into zf, then the ray's `ready` flag.
 // Fine pass: compositing into the fine outputs.
+// The ray's field values and depths (written by other CTAs: L2 loads) are first staged into the warp's shared-memory
+// scratch with coalesced loads, so the sequential transmittance / cdf loops of lane 0 run at shared-memory latency.
 __device__ __forceinline__ void finish_ray(const Params& p, int ps, int64_t ray, float* scratch, int lane) {
   const Render& rn = p.rn;
   const float* rr = rn.rays + ray * 8;
   const float near = rr[6], far = rr[7];
   const int Kc = rn.Kc, K = rn.Kc + rn.Kf;
-  if (ps == 0) {
-    if (lane == 0)
-      composite_ray(rn.zc + ray * Kc, reinterpret_cast<const float4*>(p.pass[0].out) + ray * Kc, far, Kc, rn.white,
-                    rn.wc + ray * Kc, rn.rgb_c + ray * 3, rn.depth_c + ray, LdCg(), LdCg4());
-    __syncwarp();
-    if (p.npass > 1) {
-      const int Ku = rn.Kf - rn.Kfd;
-      sample_fine_ray(near, far, rn.zc + ray * Kc, rn.wc + ray * Kc, rn.Kfd > 0 ? __ldcg(rn.depth_c + ray) : 0.f,
-                      rn.u_f + ray * Ku, rn.u_j + ray * Ku, rn.n_d + ray * rn.Kfd, rn.depth_std, rn.zf + ray * K, Kc,
-                      rn.Kf, rn.Kfd, scratch, lane, LdCg());
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(rn.ready + ray) = 1;
+  const int Kp = ps == 0 ? Kc : K;
+  const float* zg = ps == 0 ? rn.zc + ray * Kc : rn.zf + ray * K;
+  const float4* fg = reinterpret_cast<const float4*>(p.pass[ps].out) + ray * Kp;
+  float* wg = ps == 0 ? rn.wc + ray * Kc : (rn.w_f ? rn.w_f + ray * K : nullptr);
+  float* rgb = ps == 0 ? rn.rgb_c + ray * 3 : rn.rgb_f + ray * 3;
+  float* dep = ps == 0 ? rn.depth_c + ray : rn.depth_f + ray;
+  // scratch: field [Kp] float4 | z [Kp] | w [Kp] | resampling scratch [Kc + 1 + K]
+  const bool staged = (size_t)(6 * Kp + Kc + 1 + K) * sizeof(float) <= (size_t)FLUSH_SCRATCH_BYTES;
+  float4* fs = reinterpret_cast<float4*>(scratch);
+  float* zs = scratch + 4 * Kp;
+  float* ws = zs + Kp;
+  float* rs = staged ? ws + Kp : scratch;
+  if (staged) {
+    for (int k = lane; k < Kp; k += 32) {
+      fs[k] = __ldcg(fg + k);
+      zs[k] = __ldcg(zg + k);
     }
-  } else {
-    if (lane == 0)
-      composite_ray(rn.zf + ray * K, reinterpret_cast<const float4*>(p.pass[1].out) + ray * K, far, K, rn.white,
-                    rn.w_f ? rn.w_f + ray * K : nullptr, rn.rgb_f + ray * 3, rn.depth_f + ray, LdCg(), LdCg4());
     __syncwarp();
+    if (lane == 0) composite_ray(zs, fs, far, Kp, rn.white, ws, rgb, dep, LdPlain(), LdPlain4());
+    __syncwarp();
+    if (wg)
+      for (int k = lane; k < Kp; k += 32) wg[k] = ws[k];
+  } else {
+    if (lane == 0) composite_ray(zg, fg, far, Kp, rn.white, wg, rgb, dep, LdCg(), LdCg4());
+    __syncwarp();
+  }
+  if (ps == 0 && p.npass > 1) {
+    const int Ku = rn.Kf - rn.Kfd;
+    const float dc = rn.Kfd > 0 ? __ldcg(rn.depth_c + ray) : 0.f;
+    if (staged)
+      sample_fine_ray(near, far, zs, ws, dc, rn.u_f + ray * Ku, rn.u_j + ray * Ku, rn.n_d + ray * rn.Kfd, rn.depth_std,
+                      rn.zf + ray * K, Kc, rn.Kf, rn.Kfd, rs, lane, LdPlain());
+    else
+      sample_fine_ray(near, far, zg, wg, dc, rn.u_f + ray * Ku, rn.u_j + ray * Ku, rn.n_d + ray * rn.Kfd, rn.depth_std,
+                      rn.zf + ray * K, Kc, rn.Kf, rn.Kfd, rs, lane, LdCg());
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(rn.ready + ray) = 1;
   }
 }
 
@@ -477,6 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
     c.n_hi = q >> 1;                 // which 128 features of a 256-wide MMA block live in these lanes
     c.tmem = tmem_base + ((uint32_t)(32 * q) << 16);
     c.bar_base = bar_base;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(c.l2_keep));
     long long t_acc = 0;
     c.t_acc = &t_acc;
     float* scratch = p.scratch + (size_t)blockIdx.x * D * ROWS;
@@ -511,7 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
               const long long t0 = clock64();
               while (*flag == 0) {
                 if (*(volatile int*)p.status != 0) break;
-                if (clock64() - t0 > TIMEOUT_CYCLES) {
+                if (clock64() - t0 > timeout_limit(p.status)) {
                   atomicCAS(p.status, 0, 160);
                   if (((volatile int*)p.status)[1]) __trap();
                   break;
@@ -892,6 +927,8 @@ static int get_status_buffer(int** out) {
     // carry on (PNR_TC_NO_TRAP=1, for scripts/tc_debug.py which then reads the tag with pnr_tc_status)
     const int init[2] = {0, getenv("PNR_TC_NO_TRAP") ? 0 : 1};
     PNR_CUDA(cudaMemcpy(g_status[dev], init, sizeof(init), cudaMemcpyHostToDevice));
+    const int mult = getenv("PNR_TC_TIMEOUT_MULT") ? atoi(getenv("PNR_TC_TIMEOUT_MULT")) : 1;   // word 20, see timeout_limit
+    PNR_CUDA(cudaMemcpy(g_status[dev] + 20, &mult, sizeof(int), cudaMemcpyHostToDevice));
   }
   *out = g_status[dev];
   return PNR_OK;

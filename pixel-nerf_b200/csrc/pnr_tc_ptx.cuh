@@ -7,6 +7,12 @@ namespace pnr {
 namespace tcptx {
 
 constexpr long long TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: turns a protocol bug into an error, not a hang
+// status[20] multiplies the limit (PNR_TC_TIMEOUT_MULT; profilers that replay with heavy instrumentation slow a launch
+// down by two orders of magnitude)
+__device__ __forceinline__ long long timeout_limit(const int* status) {
+  const int m = ((const volatile int*)status)[20];
+  return TIMEOUT_CYCLES * (long long)(m > 1 ? m : 1);
+}
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -47,7 +53,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3F) == 0) {  // rarely: has another thread failed / did we time out?
       if (*(volatile int*)status != 0) return;
-      if (clock64() - t0 > TIMEOUT_CYCLES) {
+      if (clock64() - t0 > timeout_limit(status)) {
         atomicCAS(status, 0, tag);
         if (((volatile int*)status)[1]) __trap();   // default: fail the launch loudly (see get_status_buffer)
         return;
@@ -74,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, in
   while (!mbar_try_wait_nohint(bar, parity)) {
     if ((++spins & 0xFFF) == 0) {
       if (*(volatile int*)status != 0) break;
-      if (clock64() - t0 > TIMEOUT_CYCLES) {
+      if (clock64() - t0 > timeout_limit(status)) {
         atomicCAS(status, 0, tag);
         if (((volatile int*)status)[1]) __trap();
         break;
@@ -271,7 +277,7 @@ static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_
   while (!mbar_try_wait_cluster(bar, parity)) {
     if ((++spins & 0x3F) == 0) {
       if (*(volatile int*)status != 0) return;
-      if (clock64() - t0 > TIMEOUT_CYCLES) {
+      if (clock64() - t0 > timeout_limit(status)) {
         atomicCAS(status, 0, tag);
         if (((volatile int*)status)[1]) __trap();   // default: fail the launch loudly (see get_status_buffer)
         return;

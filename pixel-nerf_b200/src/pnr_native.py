@@ -98,16 +98,17 @@ def declare(L):
     L.pnr_project_latent_bytes.argtypes = [P(PnrScene), P(PnrMlp)]
     L.pnr_project_latent_bytes.restype = sz
     L.pnr_project_latent.argtypes = [P(PnrScene), P(PnrMlp), vp, sz, vp, sz, vp]
-    L.pnr_mgpu_create.argtypes = [P(i32), i32, P(vp)]
-    L.pnr_mgpu_destroy.argtypes = [vp]
-    L.pnr_mgpu_size.argtypes = [vp]
-    L.pnr_mgpu_size.restype = i32
-    L.pnr_mgpu_peer_store.argtypes = [vp, i32]
-    L.pnr_mgpu_peer_store.restype = i32
-    L.pnr_mgpu_broadcast.argtypes = [vp, vp, P(vp), sz, P(vp)]
-    L.pnr_mgpu_render.argtypes = [vp, P(PnrShard), P(PnrRenderCfg), vp, P(PnrRenderOut), i64, vp]
-    for name in ("pnr_mgpu_create", "pnr_mgpu_destroy", "pnr_mgpu_broadcast", "pnr_mgpu_render"):
-        getattr(L, name).restype = C.c_int
+    if hasattr(L, "pnr_mgpu_create"):     # (the host-emulator build of tests/cuda_emu has no multi-GPU driver)
+        L.pnr_mgpu_create.argtypes = [P(i32), i32, P(vp)]
+        L.pnr_mgpu_destroy.argtypes = [vp]
+        L.pnr_mgpu_size.argtypes = [vp]
+        L.pnr_mgpu_size.restype = i32
+        L.pnr_mgpu_peer_store.argtypes = [vp, i32]
+        L.pnr_mgpu_peer_store.restype = i32
+        L.pnr_mgpu_broadcast.argtypes = [vp, vp, P(vp), sz, P(vp)]
+        L.pnr_mgpu_render.argtypes = [vp, P(PnrShard), P(PnrRenderCfg), vp, P(PnrRenderOut), i64, vp]
+        for name in ("pnr_mgpu_create", "pnr_mgpu_destroy", "pnr_mgpu_broadcast", "pnr_mgpu_render"):
+            getattr(L, name).restype = C.c_int
     L.pnr_gemm_nt.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.pnr_gemm_nt.restype = C.c_int
     L.pnr_profile_begin.restype = C.c_int

@@ -18,12 +18,23 @@ def test_gen_video_main_runs_unmodified(tmp_path):
     overlay = du.make_overlay(tmp_path)
     data = du.make_srn_dataset(str(tmp_path / "data" / "cars"), n_obj=1, n_views=4, size=64)
     conf = du.write_test_conf(overlay, str(tmp_path / "test.conf"))
+    # a checkpoint for `net.load_weights(args)` (gen_video.py:104): the reference's own init zeroes every fc_1 and
+    # mostly renders sigma = 0 (a blank frame), so store the synthetic weights of the benchmarks under the name the
+    # script will look for -- this also runs the checkpoint ingest through the unmodified script
+    import gpu_util
+    import golden_util as gu
+    from model import make_model
+    net = make_model(gpu_util.model_conf(512))
+    net.mlp_coarse.load_state_dict(gu.synth.bench_mlp_weights(31, 512))
+    net.mlp_fine.load_state_dict(gu.synth.bench_mlp_weights(32, 512))
+    os.makedirs(str(tmp_path / "checkpoints" / "dropin"), exist_ok=True)
+    torch.save(net.state_dict(), str(tmp_path / "checkpoints" / "dropin" / "pixel_nerf_latest"))
     r = du.run_script(overlay, "eval/gen_video.py",
                       ["-n", "dropin", "-c", conf, "-D", data, "-F", "srn", "--split", "test", "-S", "0", "--source", "0 2",
                        "--num_views", "3", "--scale", "0.25", "--ray_batch_size", "2000", "--gpu_id", "0"],
                       cwd=tmp_path)
     assert r.returncode == 0, r.stderr[-3000:]
-    assert "Wrote to" in r.stdout
+    assert "Wrote to" in r.stdout and "Load checkpoints/dropin/pixel_nerf_latest" in r.stdout
     vids = glob.glob(str(tmp_path / "visuals" / "dropin" / "videot0000_v000_002.mp4.npy"))
     assert len(vids) == 1, os.listdir(str(tmp_path / "visuals" / "dropin"))
     frames = np.load(vids[0])
