@@ -249,7 +249,10 @@ int pnr_mgpu_render(PnrMgpu* h, const PnrShard* shards, const PnrRenderCfg* cfg,
 /* Test hook for the dense contraction the backward path is built from (nn.Linear forward / input gradient / weight
  * gradient are all this "NT" product): C[M][N] (+)= act(A[M][lda]) * W[N][K]^T (+ bias[N]), fp32 in and out.
  * engine = PNR_ENGINE_SIMT: fp32 FFMA SGEMM; PNR_ENGINE_TC (or AUTO): split-bf16 tcgen05 GEMM (3 products, fp32
- * accumulate, split-K with atomics when the output has few tiles).  K % 16 == 0, rows 16-byte aligned. */
+ * accumulate, split-K with atomics when the output has few tiles) -- the backward's engine; PNR_GEMM_F16X3: the same
+ * kernel with fp16 hi/lo operands (22 mantissa bits inside fp16's range) -- pnr_project_latent's engine.
+ * K % 16 == 0, rows 16-byte aligned. */
+#define PNR_GEMM_F16X3 3
 int pnr_gemm_nt(const float* A, int32_t lda, const float* W, const float* bias, float* C, int32_t ldc, int32_t M,
                 int32_t N, int32_t K, int32_t relu_a, int32_t accum, int32_t engine, void* stream);
 

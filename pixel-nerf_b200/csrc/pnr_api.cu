@@ -27,6 +27,8 @@ int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, 
           bool relu_a, bool accum, cudaStream_t s);                 // pnr_field_simt.cu
 int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
                 int K, bool relu_a, bool accum, cudaStream_t s);    // pnr_gemm_tc.cu
+int gemm_f16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+               cudaStream_t s);
 
 // ---- dominant-kernel profiling ----------------------------------------------------------
 static bool g_prof_on = false;
@@ -228,6 +230,10 @@ int pnr_gemm_nt(const float* A, int32_t lda, const float* W, const float* bias, 
   PNR_CHECK_ARG(A && W && C, "NULL pointer");
   PNR_CHECK_ARG(lda >= K && ldc >= N && lda % 4 == 0, "bad leading dimensions");
   if (engine == PNR_ENGINE_SIMT) return sgemm(A, lda, W, bias, C, ldc, M, N, K, relu_a != 0, accum != 0, (cudaStream_t)stream);
+  if (engine == PNR_GEMM_F16X3) {
+    PNR_CHECK_ARG(!relu_a && !accum, "the fp16-split engine is store-only without activation");
+    return gemm_f16x3(A, lda, W, K, bias, C, ldc, M, N, K, (cudaStream_t)stream);
+  }
   return gemm_bf16x3(A, lda, W, K, bias, C, ldc, M, N, K, relu_a != 0, accum != 0, (cudaStream_t)stream);
 }
 

@@ -23,6 +23,8 @@ int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, 
           bool relu_a, bool accum, cudaStream_t s);
 int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
                 int K, bool relu_a, bool accum, cudaStream_t s);   // pnr_gemm_tc.cu
+int gemm_bf16x3_masked(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, bool accum,
+                       const float* mask, cudaStream_t s);
 __global__ void k_pad_rows(const float* __restrict__ src, float* __restrict__ dst, int rows, int k_src, int k_dst);
 __global__ void k_view_mean(const float* __restrict__ X, float* __restrict__ Y, int64_t n_pts, int NS, int d);
 
@@ -407,17 +409,25 @@ int field_backward(const PnrScene& sc, const PnrMlp& mlp, const PointSource& src
       BW(transpose_pad<true>(b.nbuf[blk], d, rows_b, d, b.tB, Mp, s));
       BW(gemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc1_w[blk]), d, d, d, Mp, false, true, s));
       BW(rowsum_acc(b.tA, Mp, d, const_cast<float*>(grad.fc1_b[blk]), s));
-      BW(gemm(dh, d, b.w1T[blk], nullptr, b.T, d, rows_b, d, d, false, false, s));
-      k_mask<<<eg, 256, 0, s>>>(b.T, b.nbuf[blk], cnt);
-      PNR_LAUNCH_CHECK();
+      if (use_tc_gemm()) {   // the ReLU mask rides in the GEMM's epilogue
+        BW(gemm_bf16x3_masked(dh, d, b.w1T[blk], d, b.T, d, rows_b, d, d, false, b.nbuf[blk], s));
+      } else {
+        BW(gemm(dh, d, b.w1T[blk], nullptr, b.T, d, rows_b, d, d, false, false, s));
+        k_mask<<<eg, 256, 0, s>>>(b.T, b.nbuf[blk], cnt);
+        PNR_LAUNCH_CHECK();
+      }
       // fc_0: dW0 += dn^T relu(hpre), db0 += colsum(dn); dh += (dn W0) * (hpre > 0)
       BW(transpose_pad<false>(b.T, d, rows_b, d, b.tA, Mp, s));
       BW(transpose_pad<true>(b.hpre[blk], d, rows_b, d, b.tB, Mp, s));
       BW(gemm(b.tA, Mp, b.tB, nullptr, const_cast<float*>(grad.fc0_w[blk]), d, d, d, Mp, false, true, s));
       BW(rowsum_acc(b.tA, Mp, d, const_cast<float*>(grad.fc0_b[blk]), s));
-      BW(gemm(b.T, d, b.w0T[blk], nullptr, b.T2, d, rows_b, d, d, false, false, s));
-      k_mask_add<<<eg, 256, 0, s>>>(dh, b.T2, b.hpre[blk], cnt);
-      PNR_LAUNCH_CHECK();
+      if (use_tc_gemm()) {
+        BW(gemm_bf16x3_masked(b.T, d, b.w0T[blk], d, dh, d, rows_b, d, d, true, b.hpre[blk], s));
+      } else {
+        BW(gemm(b.T, d, b.w0T[blk], nullptr, b.T2, d, rows_b, d, d, false, false, s));
+        k_mask_add<<<eg, 256, 0, s>>>(dh, b.T2, b.hpre[blk], cnt);
+        PNR_LAUNCH_CHECK();
+      }
       if (blk < comb) {   // x = x + lin_z[blk](latent): dWz += dh^T lat, dbz += colsum(dh), dlat += dh Wz
         if (!lat_transposed) {
           BW(transpose_pad<false>(b.lat, L, R, L, b.latT, Rp, s));

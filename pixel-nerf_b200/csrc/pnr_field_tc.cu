@@ -32,6 +32,8 @@ namespace pnr {
 
 int sgemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K,
           bool relu_a, bool accum, cudaStream_t s);  // pnr_field_simt.cu
+int gemm_f16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+               cudaStream_t s);                      // pnr_gemm_tc.cu
 
 namespace tc {
 
@@ -541,19 +543,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_field
             zz = coarse_sample(rr[6], rr[7], p.rn.lin ? p.rn.lin[k] : lin_step_value(k, P.K), p.rn.u_c[pt], P.K);
             if (gsub == 0 && pt_raw < P.total_points) p.rn.zc[pt] = zz;
           } else {
-            const volatile int* flag = p.rn.ready + ray;
-            if (*flag == 0) {
-              const long long t0 = clock64();
-              while (*flag == 0) {
-                if (*(volatile int*)p.status != 0) break;
-                if (clock64() - t0 > timeout_limit(p.status)) {
-                  atomicCAS(p.status, 0, 160);
-                  if (((volatile int*)p.status)[1]) __trap();
-                  break;
+            // ONE poller per ray segment of this CTA's 64 rows (the first row of the CTA and every row that starts a
+            // ray), with back-off: pairs that run out of coarse tiles early wait here for a whole tile time, and 148 x 512
+            // threads spinning on a handful of L2 lines starve the weight stream of the pairs still computing
+            if (gsub == 0 && (k == 0 || grow == 0) && pt_raw < P.total_points) {
+              const volatile int* flag = p.rn.ready + ray;
+              if (*flag == 0) {
+                const long long t0 = clock64();
+                uint32_t spins = 0;
+                while (*flag == 0) {
+                  __nanosleep(400);
+                  if ((++spins & 0xFF) == 0) {
+                    if (*(volatile int*)p.status != 0) break;
+                    if (clock64() - t0 > timeout_limit(p.status)) {
+                      atomicCAS(p.status, 0, 160);
+                      if (((volatile int*)p.status)[1]) __trap();
+                      break;
+                    }
+                  }
                 }
               }
+              __threadfence();
             }
-            __threadfence();
+            workers_sync();   // every ray of the tile has its merged samples in L2
             zz = __ldcg(p.rn.zf + pt);
           }
           for (int i = 0; i < 3; ++i) {
@@ -1179,8 +1191,13 @@ int pnr_project_latent(const PnrScene* sc, const PnrMlp* mlp, float* proj, size_
     const float* extra = (i == 0) ? mlp->lin_in_b : mlp->fc1_b[i - 1];
     tc::k_proj_bias<<<2, 256, 0, s>>>(mlp->lin_z_b[i], extra, bias + i * tc::D, tc::D);
     PNR_LAUNCH_CHECK();
-    int rc = sgemm(sc->latent_nhwc, tc::D, mlp->lin_z_w[i], bias + i * tc::D, proj + (size_t)i * rows * tc::D, tc::D,
-                   (int)rows, tc::D, tc::D, false, false, s);
+    // fp16 hi/lo split tcgen05 GEMM (22 mantissa bits, the precision of the fused kernel's own products);
+    // PNR_PROJECT_SIMT=1 keeps the fp32 FFMA SGEMM of round 1
+    static const bool simt = getenv("PNR_PROJECT_SIMT") != nullptr;
+    int rc = simt ? sgemm(sc->latent_nhwc, tc::D, mlp->lin_z_w[i], bias + i * tc::D, proj + (size_t)i * rows * tc::D,
+                          tc::D, (int)rows, tc::D, tc::D, false, false, s)
+                  : gemm_f16x3(sc->latent_nhwc, tc::D, mlp->lin_z_w[i], tc::D, bias + i * tc::D,
+                               proj + (size_t)i * rows * tc::D, tc::D, (int)rows, tc::D, tc::D, s);
     if (rc) return rc;
   }
   return PNR_OK;

@@ -17,6 +17,7 @@
 // Roofline: tensor-bound for large K, but both operands arrive as fp32 through L2 (8 B per bf16-pair element), so
 // the practical bound is L2->SM bandwidth: 64 KB of operands per 6.3 M MAC k-step.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "pnr_common.cuh"
@@ -38,8 +39,9 @@ constexpr int NPROD_WARPS = 8;
 constexpr int NTHREADS = (NPROD_WARPS + 1) * 32;
 constexpr int SM_BAR = STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = SM_BAR + 256;
-// kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16: D = F32 (bit 4), A / B format BF16 (bits 7, 10 set) or F16 (clear), both K-major, N = 128, M = 128
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_BF16 = IDESC_F16 | (1u << 7) | (1u << 10);
 
 struct Params {
   const float* A;
@@ -49,9 +51,14 @@ struct Params {
   int lda, ldw, ldc, M, N, K;
   int k_per_split;   // multiple of BK
   int relu_a, mode;  // mode 0: store, 1: C += (single split), 2: atomic add (split-K)
+  const float* mask; // optional [M][ldc]: the product is zeroed where mask <= 0 (ReLU backward) before store / add
   int* status;
 };
 
+// 8 fp32 values -> error-compensated 16-bit pairs x = hi + lo.  BF16: 8 + 8 mantissa bits with fp32's exponent range
+// (gradient-sized values need no scaling).  F16: 11 + 11 bits for values inside fp16's range (|x| < 65504; low parts
+// below 6e-5 go subnormal, i.e. an ABSOLUTE error floor of 3e-8): the per-encode projection of the latent.
+template <bool BF16>
 __device__ __forceinline__ void split8(const float4 a, const float4 b, bool relu, uint4& hi, uint4& lo) {
   float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   uint32_t h[4], l[4];
@@ -62,16 +69,24 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, bool relu
       x0 = fmaxf(x0, 0.f);
       x1 = fmaxf(x1, 0.f);
     }
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(x1), "f"(x0));
-    const float r0 = x0 - __uint_as_float(h[i] << 16);
-    const float r1 = x1 - __uint_as_float(h[i] & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
+    if (BF16) {
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(x1), "f"(x0));
+      const float r0 = x0 - __uint_as_float(h[i] << 16);
+      const float r1 = x1 - __uint_as_float(h[i] & 0xFFFF0000u);
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
+    } else {
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(x1), "f"(x0));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    }
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_bf16x3(const __grid_constant__ Params p) {
+template <bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_split3(const __grid_constant__ Params p) {
+  constexpr uint32_t IDESC = BF16 ? IDESC_BF16 : IDESC_F16;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_u = smem_u32(smem);
@@ -139,10 +154,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_bf16x3(const __grid_consta
         const int id = t + 256 * i, row = id >> 3, u = id & 7;
         const uint32_t off = (uint32_t)(row * 128 + ((u ^ (row & 7)) * 16));
         uint4 hi, lo;
-        split8(va[i][0], va[i][1], p.relu_a != 0, hi, lo);
+        split8<BF16>(va[i][0], va[i][1], p.relu_a != 0, hi, lo);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + TILE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
-        split8(vb[i][0], vb[i][1], false, hi, lo);
+        split8<BF16>(vb[i][0], vb[i][1], false, hi, lo);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + 2 * TILE_BYTES + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + 3 * TILE_BYTES + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
       }
@@ -165,6 +180,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_bf16x3(const __grid_consta
       if (m < p.M) {
         float* dst = p.C + (size_t)m * p.ldc + nb;
         const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+        if (p.mask) {
+          const float* mk = p.mask + (size_t)m * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < p.N && !(mk[j] > 0.f)) v[j] = 0.f;
+        }
         if (nb + 16 <= p.N && p.mode != 2 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -228,19 +249,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_bf16x3(const __grid_consta
 
 }  // namespace gemmtc
 
-// Same contract as sgemm() (pnr_field_simt.cu) plus `ldw` (row stride of W).  K % 16 == 0, 16-byte aligned rows.
-int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
-                int K, bool relu_a, bool accum, cudaStream_t s) {
+static int gemm_split3(bool bf16, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                       int M, int N, int K, bool relu_a, bool accum, const float* mask, cudaStream_t s) {
   using namespace gemmtc;
   if (M == 0 || N == 0) return PNR_OK;
   if (K % 16 != 0 || lda % 4 != 0 || ldw % 4 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)W & 15)) {
-    set_error("gemm_bf16x3: K must be a multiple of 16 and the operands 16-byte aligned");
+    set_error("tensor-core gemm: K must be a multiple of 16 and the operands 16-byte aligned");
     return PNR_ERR_INVALID;
   }
   Params p;
   p.A = A; p.W = W; p.bias = bias; p.C = C;
   p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.relu_a = relu_a ? 1 : 0;
+  p.mask = mask;
+  if (mask && bias) {
+    set_error("tensor-core gemm: mask and bias together are not supported");
+    return PNR_ERR_INVALID;
+  }
   int rc = tc_status_buffer(&p.status);
   if (rc) return rc;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -261,15 +286,33 @@ int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* b
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    PNR_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PNR_CUDA(cudaFuncSetAttribute(k_gemm_split3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PNR_CUDA(cudaFuncSetAttribute(k_gemm_split3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set[dev] = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
   prof_before(s);
-  k_gemm_bf16x3<<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+  if (bf16) k_gemm_split3<true><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
+  else k_gemm_split3<false><<<grid, NTHREADS, SMEM_BYTES, s>>>(p);
   prof_after(s);
   PNR_LAUNCH_CHECK();
   return PNR_OK;
+}
+
+// Same contract as sgemm() (pnr_field_simt.cu) plus `ldw` (row stride of W).  K % 16 == 0, 16-byte aligned rows.
+int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                int K, bool relu_a, bool accum, cudaStream_t s) {
+  return gemm_split3(true, A, lda, W, ldw, bias, C, ldc, M, N, K, relu_a, accum, nullptr, s);
+}
+// ... with the ReLU-backward mask fused into the epilogue: C (+)= (A W^T) * (mask > 0), mask laid out like C
+int gemm_bf16x3_masked(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, bool accum,
+                       const float* mask, cudaStream_t s) {
+  return gemm_split3(true, A, lda, W, ldw, nullptr, C, ldc, M, N, K, false, accum, mask, s);
+}
+// fp16 hi/lo operands (22 mantissa bits inside fp16's range): the per-encode projection of the latent
+int gemm_f16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+               cudaStream_t s) {
+  return gemm_split3(false, A, lda, W, ldw, bias, C, ldc, M, N, K, false, false, nullptr, s);
 }
 
 }  // namespace pnr

@@ -1,5 +1,7 @@
 // TEST INFRASTRUCTURE: the tensor-engine entry points are not emulated (tcgen05 has no host meaning); the emulated
 // library reports the tensor engine as unavailable so that every call takes the SIMT path.
+#include <vector>
+
 #include "pnr_common.cuh"
 
 namespace pnr {
@@ -26,6 +28,24 @@ int gemm_bf16x3(const float* A, int lda, const float* W, int ldw, const float* b
     return PNR_ERR_INVALID;
   }
   return sgemm(A, lda, W, bias, C, ldc, M, N, K, relu_a, accum, s);
+}
+int gemm_f16x3(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+               cudaStream_t s) {
+  return gemm_bf16x3(A, lda, W, ldw, bias, C, ldc, M, N, K, false, false, s);
+}
+// C (+)= (A W^T) * (mask > 0): emulated launches run synchronously on host memory, so a host temporary does
+int gemm_bf16x3_masked(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K, bool accum,
+                       const float* mask, cudaStream_t s) {
+  std::vector<float> tmp((size_t)M * N);
+  int rc = gemm_bf16x3(A, lda, W, ldw, nullptr, tmp.data(), N, M, N, K, false, false, s);
+  if (rc) return rc;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      const float v = mask[(size_t)m * ldc + n] > 0.f ? tmp[(size_t)m * N + n] : 0.f;
+      float& c = C[(size_t)m * ldc + n];
+      c = accum ? c + v : v;
+    }
+  return PNR_OK;
 }
 }  // namespace pnr
 

@@ -109,6 +109,24 @@ def test_fused_training_step_matches_the_reference_gradients(name):
             assert rel(p.grad.cpu(), g["gf"][k]) < 1e-3, ("fine", k)
 
 
+def test_gemm_nt_fp16_split_engine():
+    """The projection's engine (fp16 hi/lo operands): latent-sized values times kaiming-sized weights, 22 mantissa bits."""
+    import gpu_util  # noqa: F401
+    import pnr_native as pn
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1000, 512, 512
+    A = torch.clamp_min(torch.randn(M, K, generator=g) * 19 + 4, 0).to(dev)      # synth.make_latent statistics
+    W = (torch.randn(N, K, generator=g) * 0.0625).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    C = torch.zeros(M, N, device=dev)
+    pn.check(pn.lib().pnr_gemm_nt(pn.dptr(A), K, pn.dptr(W), pn.dptr(b), pn.dptr(C), N, M, N, K, 0, 0, 3, pn.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    scale = (A.double().abs() @ W.double().abs().t()).max()
+    assert ((C.double() - ref).abs().max() / scale) < 2e-6
+
+
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 @pytest.mark.parametrize("M,N,K,relu,accum", [(300, 512, 512, True, False),     # forward layer, ragged M
                                                (512, 512, 4000, False, True),    # weight gradient: K = rows, split-K
