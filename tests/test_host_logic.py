@@ -34,13 +34,43 @@ def test_hocon_subset():
         c.get_int("missing")
 
 
-@pytest.mark.parametrize("name", ["srn", "sn64", "dtu"])
+@pytest.mark.parametrize("name", ["srn", "sn64", "dtu", "sn64_unseen", "multi_obj"])
 def test_conf_files_resolve_includes(name):
     c = hocon.parse_file(os.path.join(PKG, "conf", "exp", name + ".conf"))
     assert c.get_int("model.mlp_coarse.n_blocks") == 5 and c.get_int("model.mlp_coarse.combine_layer") == 3
     assert c.get_int("renderer.n_coarse") == 64 and c.get_list("renderer.sched") == []
     assert c.get_float("renderer.white_bkgd") == (0.0 if name == "dtu" else 1.0)
-    assert c.get_bool("model.encoder.use_first_pool", True) == (name != "sn64")
+    assert c.get_bool("model.encoder.use_first_pool", True) == (name not in ("sn64", "sn64_unseen"))
+    assert c.get_string("data.format") == {"srn": "srn", "sn64": "dvr", "dtu": "dvr_dtu", "sn64_unseen": "dvr_gen",
+                                           "multi_obj": "multi_obj"}[name]
+
+
+def _flatten(c, prefix=""):
+    out = {}
+    for k in c.keys():
+        v = c[k]
+        if hasattr(v, "keys"):
+            out.update(_flatten(v, prefix + k + "."))
+        else:
+            out[prefix + k] = v
+    return out
+
+
+def test_shipped_confs_equal_the_reference_confs():
+    """Every exp conf and expconf.conf of this package parses to the same tree as the reference's own file (read with
+    the same in-repo HOCON reader; the reference's files are the schema)."""
+    ref = None
+    for root in (os.environ.get("PIXELNERF_REF"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if root and os.path.isdir(os.path.join(root, "conf", "exp")):
+            ref = root
+            break
+    if ref is None:
+        pytest.skip("no reference checkout")
+    for name in sorted(os.listdir(os.path.join(ref, "conf", "exp"))):
+        ours = hocon.parse_file(os.path.join(PKG, "conf", "exp", name))
+        theirs = hocon.parse_file(os.path.join(ref, "conf", "exp", name))
+        assert _flatten(ours) == _flatten(theirs), name
+    assert _flatten(hocon.parse_file(os.path.join(PKG, "expconf.conf"))) == _flatten(hocon.parse_file(os.path.join(ref, "expconf.conf")))
 
 
 def test_model_state_dict_keys_and_shapes():
@@ -75,6 +105,31 @@ def test_unsupported_flags_raise_by_name():
     from render import NeRFRenderer
     with pytest.raises(NotImplementedError, match="lindisp"):
         NeRFRenderer(lindisp=True)
+    # the fused kernels compute the shipped positional code (6 frequencies x 1.5, input included) in registers:
+    # any other code is refused by name instead of being trained with one encoding and rendered with another
+    for key, val in (("code.freq_factor", 3.14159), ("code.num_freqs", 4), ("code.include_input", False)):
+        conf = gpu_util.model_conf(32)
+        conf.put(key, val)
+        with pytest.raises((NotImplementedError, AssertionError, RuntimeError), match="code|size|shape|mat1"):
+            make_model(conf)
+
+
+def test_scene_epoch_and_contiguous_camera_state():
+    """encode() / set_scene() bump the epoch that keys per-GPU replicas, and the camera buffers whose raw pointers go
+    to the kernels are contiguous whatever layout the caller's focal / c tensors have."""
+    from model import make_model
+    net = make_model(gpu_util.model_conf(32)).eval()
+    e0 = net._scene_epoch
+    poses = torch.eye(4).repeat(2, 2, 1, 1)
+    focal = (torch.rand(2, 4) * 10 + 30)[:, ::2]      # non-contiguous (SB, 2) view
+    c = torch.rand(2, 4)[:, 1::2]                      # non-contiguous (SB, 2) view
+    net.set_scene(torch.rand(4, 512, 8, 8), poses, focal, c, 16, 16)
+    assert net._scene_epoch == e0 + 1
+    assert net.focal.is_contiguous() and net.c.is_contiguous() and net.poses.is_contiguous()
+    assert not focal.is_contiguous() and not c.is_contiguous()
+    assert torch.equal(net.focal[:, 1], -focal[:, 1]) and torch.equal(net.c, c)
+    net.set_cameras(poses.reshape(-1, 4, 4), focal, c, 16, 16)
+    assert net._scene_epoch == e0 + 2
 
 
 def test_renderer_conf_schedule_and_state():
