@@ -1,3 +1,7 @@
+"""Debug helper: one small tensor-engine field evaluation against the oracle.  Run with PNR_TC_NO_TRAP=1 so that a
+barrier timeout records its tag (printed as `status`) instead of trapping the launch."""
+import os
+os.environ.setdefault("PNR_TC_NO_TRAP", "1")
 import sys, os, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, "pixel-nerf_b200/src")
 import golden_util as gu, gpu_util, pnr_native as pn
