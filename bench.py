@@ -347,7 +347,10 @@ def run_ours(args):
     parity = None
     cpu_base = None
     if rank == 0 and not args.no_parity:
-        parity = parity_block(net, renderer, cfg, rays_dev)
+        try:
+            parity = parity_block(net, renderer, cfg, rays_dev)
+        except Exception as e:     # the throughput line must still be printed
+            parity = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_subprocess(args.workload, args.cpu_rays or wl["cpu_rays"])
 
