@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pixel-nerf_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-UNITS = ["pnr_api.cu", "pnr_stages.cu", "pnr_field_simt.cu", "pnr_field_bwd.cu"]
+UNITS = ["pnr_api.cu", "pnr_stages.cu", "pnr_field_simt.cu", "pnr_field_bwd.cu", "pnr_mgpu.cu"]
 LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^;{}()]*?>)?)\s*<<<(.+?)>>>\s*\((.*?)\);", re.S)
 
 

@@ -49,6 +49,23 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+// ---- what csrc/pnr_mgpu.cu uses: ONE emulated device, every "peer" is the host heap, all work is synchronous -------
+enum { cudaMemcpyDefault = 4, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaErrorPeerAccessAlreadyEnabled = 704 };
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 64 ? cudaSuccess : cudaErrorUnknown; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int a, int b) { *can = (a != b); return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int, cudaStream_t) {
+  for (size_t r = 0; r < h; ++r) memcpy(static_cast<char*>(d) + r * dp, static_cast<const char*>(s) + r * sp, w);
+  return cudaSuccess;
+}
 
 namespace emu {
 // ---- cooperative threads as fibers on ONE OS thread (x86-64): deterministic, no futex storms ----------------------
